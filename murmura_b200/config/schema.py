@@ -1,0 +1,135 @@
+"""Pydantic config schema — a superset of the reference's (``murmura/config/schema.py:7-202``).
+
+Every reference block/field/default is kept (so reference YAMLs load unchanged; unknown
+top-level keys are rejected, unknown keys inside blocks ignored).  Additions are purely
+additive: ``backend: "b200"`` and the optional ``b200:`` block that configures the
+Blackwell engine (GPU count, transport, CUDA graphs, compute dtype, sketch precision…).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Literal, Optional
+
+from pydantic import BaseModel, ConfigDict, Field
+
+
+class DistributedConfig(BaseModel):
+    """ZeroMQ wall-clock backend settings (reference ``schema.py:7-51``)."""
+    transport: Literal["ipc", "tcp"] = Field(default="ipc", description="ipc (one host) or tcp (multi-host)")
+    ipc_dir: str = Field(default="/tmp/murmura", description="base directory of the IPC socket files")
+    host: str = Field(default="127.0.0.1", description="coordinator host for tcp transport")
+    coordinator_pub_port: int = Field(default=5500, description="kept for schema parity (unused)")
+    coordinator_pull_port: int = Field(default=5501, description="monitor PULL port (tcp)")
+    base_port: int = Field(default=5550, description="node i listens on base_port + i (tcp)")
+    node_hosts: Optional[Dict[int, str]] = Field(default=None, description="per-node host overrides (tcp)")
+    round_duration_s: float = Field(default=60.0, description="wall-clock budget of one round")
+    startup_grace_s: float = Field(default=5.0, description="delay between launch and round 0")
+
+
+class ExperimentConfig(BaseModel):
+    name: str = Field(description="experiment name")
+    seed: int = Field(default=42)
+    rounds: int = Field(default=20)
+    verbose: bool = Field(default=False)
+
+
+class TopologyConfig(BaseModel):
+    type: Literal["ring", "fully", "erdos", "k-regular"]
+    num_nodes: int
+    p: Optional[float] = Field(default=None, description="edge probability (erdos)")
+    k: Optional[int] = Field(default=None, description="degree (k-regular)")
+    seed: int = Field(default=12345)
+
+
+class AggregationConfig(BaseModel):
+    algorithm: Literal["fedavg", "krum", "balance", "sketchguard", "ubar", "evidential_trust"]
+    params: Dict[str, Any] = Field(default_factory=dict)
+
+
+class AttackConfig(BaseModel):
+    enabled: bool = False
+    type: Optional[Literal["gaussian", "directed_deviation", "topology_liar"]] = None
+    percentage: float = 0.0
+    params: Dict[str, Any] = Field(default_factory=dict)
+
+
+class MobilityConfig(BaseModel):
+    area_size: float = 100.0
+    comm_range: float = 30.0
+    max_speed: float = 5.0
+    seed: int = 42
+    ensure_connected: bool = True
+
+
+class DMTTConfig(BaseModel):
+    """DMTT hyper-parameters (reference ``schema.py:114-139``)."""
+    budget_B: int = 5
+    rho: float = 0.1
+    lambda_forget: float = 0.9
+    w_d: float = 1.0
+    w_c: float = 0.5
+    w_x: float = 1.0
+    tau_U: float = 0.3
+    eta: float = 5.0
+    w_a: float = 0.7
+    tau_u: float = 0.5
+    lambda1: float = 0.4
+    lambda2: float = 0.3
+    lambda3: float = 0.2
+    lambda4: float = 0.1
+
+
+class TrainingConfig(BaseModel):
+    local_epochs: int = 1
+    batch_size: int = 64
+    lr: float = 0.01
+    max_samples: Optional[int] = None
+
+
+class DataConfig(BaseModel):
+    adapter: str
+    params: Dict[str, Any] = Field(default_factory=dict)
+
+
+class ModelConfig(BaseModel):
+    factory: str
+    params: Dict[str, Any] = Field(default_factory=dict)
+
+
+class B200Config(BaseModel):
+    """Blackwell engine knobs (new; all optional)."""
+    gpus: Optional[int] = Field(default=None, description="GPUs to use; default WORLD_SIZE or 1")
+    transport: Literal["p2p", "nvls", "nccl"] = Field(
+        default="p2p", description="p2p = in-kernel peer loads (product); nvls = multimem "
+        "reduce for full-mesh FedAvg; nccl = baseline send/recv + PyTorch aggregation")
+    cuda_graphs: bool = Field(default=True, description="capture per-node train/eval steps in CUDA graphs")
+    compute_dtype: Literal["fp32", "tf32", "bf16"] = Field(
+        default="tf32", description="matmul/conv math mode for local training (params stay fp32)")
+    sketch_dtype: Literal["fp32", "fp8"] = Field(
+        default="fp32", description="published Count-Sketch precision (fp8 = e4m3 + ue8m0 per 32)")
+    krum_gram: Literal["auto", "tcgen05", "fp32"] = Field(
+        default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
+    streams: int = Field(default=4, description="concurrent CUDA streams for virtual-node training")
+    eval_batch: int = Field(default=1024, description="evaluation micro-batch (results are batch-size independent)")
+    flag_timeout_ms: float = Field(default=5000.0, description="device-side wait budget for a peer's publish flag")
+    fault_drop_edges: Dict[int, list] = Field(
+        default_factory=dict, description="fault injection: {round: [[src, dst], ...]} edges to drop")
+    checkpoint_every: int = Field(default=0, description="save arena checkpoint every k rounds (0 = off)")
+    checkpoint_dir: str = Field(default="checkpoints")
+    profile: bool = Field(default=False, description="emit NVTX ranges + per-phase CUDA-event timings")
+
+
+class Config(BaseModel):
+    model_config = ConfigDict(extra="forbid")
+
+    experiment: ExperimentConfig
+    topology: TopologyConfig
+    aggregation: AggregationConfig
+    attack: AttackConfig = Field(default_factory=AttackConfig)
+    training: TrainingConfig
+    data: DataConfig
+    model: ModelConfig
+    backend: Literal["simulation", "distributed", "b200"] = Field(default="simulation")
+    distributed: DistributedConfig = Field(default_factory=DistributedConfig)
+    mobility: Optional[MobilityConfig] = None
+    dmtt: Optional[DMTTConfig] = None
+    b200: B200Config = Field(default_factory=B200Config)
