@@ -35,14 +35,14 @@ SHAPES: Dict[str, Tuple[Tuple[int, ...], int]] = {
 
 
 def make_synthetic_tensors(name: str, num_samples: int, seed: int = 0, noise: float = 1.0,
-                           latent_dim: int = 32) -> Tuple[torch.Tensor, torch.Tensor]:
+                           latent_dim: int = 32, separation: float = 0.6) -> Tuple[torch.Tensor, torch.Tensor]:
     """Deterministic ``(X float32, y int64)`` for workload ``name``."""
     if name not in SHAPES:
         raise ValueError(f"unknown synthetic workload '{name}' (have {sorted(SHAPES)})")
     shape, classes = SHAPES[name]
     dim = int(np.prod(shape))
     g = torch.Generator().manual_seed(1_000_003 * seed + 17)
-    protos = torch.randn(classes, latent_dim, generator=g) * 2.0
+    protos = torch.randn(classes, latent_dim, generator=g) * separation
     lift = torch.randn(latent_dim, dim, generator=g) / latent_dim ** 0.5
     y = torch.randint(0, classes, (num_samples,), generator=g)
     z = protos[y] + noise * torch.randn(num_samples, latent_dim, generator=g)
@@ -59,9 +59,10 @@ class SyntheticAdapter(DatasetAdapter):
 
     def __init__(self, name: str = "mnist", num_nodes: int = 8, samples_per_node: int = 512,
                  partition_method: str = "dirichlet", alpha: float = 0.5, seed: int = 42,
-                 noise: float = 1.0, min_samples_per_client: int = 2,
+                 noise: float = 1.0, separation: float = 0.6, min_samples_per_client: int = 2,
                  max_samples: Optional[int] = None, **_unused):
-        x, y = make_synthetic_tensors(name, num_nodes * samples_per_node, seed=seed, noise=noise)
+        x, y = make_synthetic_tensors(name, num_nodes * samples_per_node, seed=seed, noise=noise,
+                                      separation=separation)
         if partition_method == "dirichlet":
             parts = dirichlet_partition(y.numpy(), num_nodes, alpha=alpha,
                                         min_samples_per_client=min_samples_per_client, seed=seed)
