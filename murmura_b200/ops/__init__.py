@@ -1,2 +1,131 @@
-def available():
-    return False
+"""sm_100a CUDA extension: build, load and thin Python wrappers.
+
+The extension is compiled **in-tree** (``murmura_b200/ops/_build/murmura_b200_ext.so``) with
+``nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo`` so the binary travels with the repo to
+GPU boxes.  ``available()`` is True only when the ``.so`` is loaded *and* a CUDA device exists; on a
+GPU machine a missing extension is a hard error for the B200 engine (no silent eager fallback).
+
+Every wrapper has a plain-PyTorch oracle in :mod:`murmura_b200.ops.reference` used by the tests.
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib.machinery
+import importlib.util
+import os
+import sys
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+_SRC = _HERE / "csrc"
+_BUILD = _HERE / "_build"
+_NAME = "murmura_b200_ext"
+_SOURCES = ["bindings.cpp", "arena.cu", "aggregate.cu", "train.cu", "gram_tcgen05.cu", "dmtt.cu"]
+_CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--use_fast_math",
+               "-std=c++17", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+_ext = None
+_load_error: Optional[str] = None
+
+
+def _source_digest() -> str:
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(_SRC)):
+        h.update(name.encode())
+        h.update((_SRC / name).read_bytes())
+    h.update(" ".join(_CUDA_FLAGS).encode())
+    h.update(torch.__version__.encode())
+    return h.hexdigest()[:16]
+
+
+def _so_path() -> Path:
+    return _BUILD / f"{_NAME}.so"
+
+
+def _import_so(path: Path):
+    loader = importlib.machinery.ExtensionFileLoader(_NAME, str(path))
+    spec = importlib.util.spec_from_loader(_NAME, loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    sys.modules[_NAME] = mod
+    return mod
+
+
+def build_extension(verbose: bool = False, force: bool = False) -> str:
+    """Compile the extension for sm_100a (cross-compiles without a GPU). Returns the .so path."""
+    from torch.utils import cpp_extension
+    _BUILD.mkdir(exist_ok=True)
+    stamp = _BUILD / "stamp.txt"
+    digest = _source_digest()
+    if not force and _so_path().exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        return str(_so_path())
+    os.environ.setdefault("MAX_JOBS", str(min(8, os.cpu_count() or 4)))
+    cpp_extension.load(
+        name=_NAME, sources=[str(_SRC / s) for s in _SOURCES], build_directory=str(_BUILD),
+        extra_cuda_cflags=_CUDA_FLAGS, extra_cflags=["-O3", "-std=c++17"], verbose=verbose, is_python_module=False)
+    stamp.write_text(digest)
+    return str(_so_path())
+
+
+def load(required: bool = False):
+    """Load the prebuilt ``.so`` (building it first if sources changed and nvcc is present)."""
+    global _ext, _load_error
+    if _ext is not None:
+        return _ext
+    try:
+        stamp = _BUILD / "stamp.txt"
+        fresh = _so_path().exists() and stamp.exists() and stamp.read_text().strip() == _source_digest()
+        if not fresh:
+            build_extension()
+        _ext = _import_so(_so_path())
+    except Exception as exc:  # noqa: BLE001 - surfaced through required / load_error()
+        _load_error = f"{type(exc).__name__}: {exc}"
+        if required:
+            raise RuntimeError(f"murmura_b200 CUDA extension unavailable: {_load_error}") from exc
+    return _ext
+
+
+def load_error() -> Optional[str]:
+    return _load_error
+
+
+def available() -> bool:
+    """True when kernels can actually run (CUDA device present and extension loaded)."""
+    return torch.cuda.is_available() and load() is not None
+
+
+def ext():
+    """The loaded extension module; raises loudly when it is missing."""
+    mod = load(required=True)
+    return mod
+
+
+# ---- autograd wrapper: fused evidential loss -------------------------------------------------------
+
+class _EvidentialLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha: torch.Tensor, targets: torch.Tensor, lam):
+        lam_t = lam if isinstance(lam, torch.Tensor) else None
+        loss, grad = ext().evidential_loss_fwd_bwd(alpha.contiguous().float(), targets.contiguous(),
+                                                   0.0 if lam_t is not None else float(lam), lam_t)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def evidential_loss(alpha: torch.Tensor, targets: torch.Tensor, lam) -> torch.Tensor:
+    """Fused forward+backward evidential loss (``train.cu::evidential_loss_kernel``).
+
+    ``lam`` is a Python float or a 0-dim CUDA tensor (read on the device, so a CUDA graph that
+    captured the loss follows the annealing schedule without re-capture)."""
+    return _EvidentialLossFn.apply(alpha, targets, lam)
+
+
+__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss"]

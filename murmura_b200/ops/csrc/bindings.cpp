@@ -1,0 +1,88 @@
+// murmura_b200 — Python bindings of the sm_100a extension.
+#include <torch/extension.h>
+#include <pybind11/stl.h>
+
+namespace py = pybind11;
+using torch::Tensor;
+
+void bind_arena(py::module_& m);
+
+// aggregate.cu
+void publish(Tensor live, int64_t pub_ptr, int64_t stride, int64_t V, int64_t Pf, int64_t Pf_pad, c10::optional<Tensor> ints,
+             Tensor scale, Tensor noise_std, Tensor node_gid, int64_t seed, int64_t round, int64_t peer_flags_ptr,
+             int64_t G, int64_t my_rank, int64_t epoch, Tensor ticket);
+void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr,
+                     Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, int64_t len, bool renorm,
+                     int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
+void wait_epoch(Tensor anchor, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
+void tail_blend(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
+                Tensor src_slot, Tensor mask, Tensor w_tail, int64_t Pf_pad, Tensor ints, int64_t timed_out_ptr);
+void edge_distances(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
+                    Tensor src_slot, Tensor mask, int64_t len, Tensor d2, Tensor n2, int64_t flags_ptr, int64_t G, int64_t epoch,
+                    double timeout_ms, int64_t timed_out_ptr);
+void pairwise_distances(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
+                        Tensor src_slot, Tensor mask, int64_t len, Tensor D, int64_t max_m, int64_t flags_ptr, int64_t G, int64_t epoch,
+                        double timeout_ms, int64_t timed_out_ptr);
+void count_sketch(int64_t base_ptr, int64_t stride, Tensor slots, Tensor table, int64_t Pf, int64_t K, Tensor out);
+void sketch_quant_mxfp8(Tensor sk, int64_t q_ptr, int64_t sc_ptr, int64_t Kpad);
+void fedavg_weights(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats);
+void balance_filter(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats,
+                    Tensor d2, Tensor n2, Tensor dist_out, double factor, double alpha, int64_t min_neighbors, int64_t timed_out_ptr);
+void sketchguard_filter(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats,
+                        Tensor own_sketch, int64_t peer_sketch_ptr, int64_t peer_q_ptr, int64_t peer_sc_ptr, int64_t plane_slots,
+                        int64_t K, int64_t Kpad, bool fp8, double factor, double alpha, int64_t min_neighbors, Tensor hist,
+                        Tensor dist_out, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
+void ubar_stage1(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats,
+                 Tensor d2, double rho, int64_t min_neighbors, Tensor cand, Tensor rank, int64_t timed_out_ptr);
+void ubar_stage2(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats,
+                 Tensor cand, Tensor rank, Tensor loss, Tensor own_loss, double alpha, bool use_loss);
+void krum_select(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats,
+                 Tensor D, int64_t num_compromised, Tensor winner, int64_t timed_out_ptr);
+void trust_filter(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats,
+                  Tensor vac, Tensor acc, Tensor src_gid, int64_t N, Tensor ema, Tensor ema_valid, double accuracy_weight,
+                  double vacuity_threshold, double momentum, bool adaptive, double threshold, double self_weight, Tensor trust_out,
+                  int64_t timed_out_ptr);
+// train.cu
+void sgd_step(Tensor live, int64_t stride, Tensor grad, int64_t gstride, int64_t slot0, int64_t nslots, int64_t n, double lr);
+void ce_eval(Tensor logits, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats);
+void dirichlet_eval(Tensor alpha, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats);
+std::vector<Tensor> evidential_loss_fwd_bwd(Tensor alpha, Tensor targets, double lam, c10::optional<Tensor> lam_t);
+// gram_tcgen05.cu
+Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_stride, int64_t row_len, int64_t box_rows);
+void gram_tf32(Tensor maps_cpu, std::vector<int64_t> box_map, std::vector<int64_t> box_y, int64_t box_rows, int64_t kb0,
+               int64_t kb1, int64_t R, Tensor out, bool zero_out, int64_t max_ctas);
+// dmtt.cu
+void mobility_adjacency(Tensor pos, int64_t round, double area, double range, bool ensure_connected, Tensor adj);
+void liar_claims(Tensor adj, Tensor is_liar, Tensor claims);
+void dmtt_update(Tensor adj, Tensor claims, Tensor collab, Tensor received, Tensor model_score, Tensor score_valid, Tensor c_hat,
+                 Tensor alpha, Tensor beta, Tensor next_collab, Tensor q_out, double rho, double lam, double w_d, double w_x,
+                 double tau_U, double eta, double l1, double l2, double l3, int64_t B, int64_t node0);
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "murmura_b200 sm_100a kernels";
+    bind_arena(m);
+    m.def("publish", &publish);
+    m.def("weighted_gather", &weighted_gather);
+    m.def("tail_blend", &tail_blend);
+    m.def("wait_epoch", &wait_epoch);
+    m.def("edge_distances", &edge_distances);
+    m.def("pairwise_distances", &pairwise_distances);
+    m.def("count_sketch", &count_sketch);
+    m.def("sketch_quant_mxfp8", &sketch_quant_mxfp8);
+    m.def("fedavg_weights", &fedavg_weights);
+    m.def("balance_filter", &balance_filter);
+    m.def("sketchguard_filter", &sketchguard_filter);
+    m.def("ubar_stage1", &ubar_stage1);
+    m.def("ubar_stage2", &ubar_stage2);
+    m.def("krum_select", &krum_select);
+    m.def("trust_filter", &trust_filter);
+    m.def("sgd_step", &sgd_step);
+    m.def("ce_eval", &ce_eval);
+    m.def("dirichlet_eval", &dirichlet_eval);
+    m.def("evidential_loss_fwd_bwd", &evidential_loss_fwd_bwd);
+    m.def("gram_tf32", &gram_tf32);
+    m.def("gram_make_maps", &gram_make_maps);
+    m.def("mobility_adjacency", &mobility_adjacency);
+    m.def("liar_claims", &liar_claims);
+    m.def("dmtt_update", &dmtt_update);
+}

@@ -1,0 +1,258 @@
+// murmura_b200 — pairwise-distance Gram matrix on 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces the all-pairs L2 loop of Krum (reference murmura/aggregation/krum.py:55-62 via
+// murmura/aggregation/base.py:118-135: m² per-key torch.norm calls with .item() host syncs).
+//
+//   G = X·Xᵀ,  X ∈ R^{R×P}  (R ≤ 128 model states, P up to 60 M parameters), dist²_ab = G_aa + G_bb − 2·G_ab
+//
+// This is a skinny-M/N, enormous-K GEMM, i.e. purely bandwidth bound: every fp32 parameter tile is pulled
+// ONCE (from local HBM or from a peer GPU's published buffer over NVLink — the tensor maps point at
+// peer-mapped addresses) by TMA straight into 128B-swizzled shared memory and consumed in place by
+// `tcgen05.mma.kind::tf32` as BOTH the A and the B operand (same smem descriptor), accumulating a
+// 128×N fp32 tile in TMEM.  Split-K over a persistent grid (one CTA per SM), partial tiles are merged
+// with fp32 reductions into the R×R result.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (tcgen05.ld → red.global.add).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mb {
+
+constexpr int kGramRows = 128;                 // UMMA M (tile rows; unused rows are ignored)
+constexpr int kGramKB = 32;                    // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int kGramStages = 6;
+constexpr int kStageBytes = kGramRows * kGramKB * 4;   // 16 KiB
+constexpr int kMaxBoxes = 16;
+constexpr int kMaxMaps = 16;
+constexpr int kGramThreads = 192;
+
+struct GramMaps { CUtensorMap m[kMaxMaps]; };
+struct GramBoxes { int n; int rows; int map[kMaxBoxes]; int y[kMaxBoxes]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 22)) __trap();        // never hang the GPU: a lost arrival aborts the kernel instead
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// K-major operand, 128-byte swizzle: rows are 128 B, 8-row groups are 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address  [0,14)
+    d |= (uint64_t)0 << 16;                                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                                  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                  // layout: SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major.
+__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramBoxes boxes, int kb0, int kb1, int n_mma, int R,
+                 float* __restrict__ out /*[128][128]*/) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kGramStages];
+    __shared__ __align__(8) uint64_t empty_bar[kGramStages];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // split-K: contiguous chunk of k-blocks per CTA
+    const int total = kb1 - kb0;
+    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my0 = kb0 + (int)blockIdx.x * per;
+    const int my1 = min(kb1, my0 + per);
+    const int num_kb = max(0, my1 - my0);
+
+    if (warp == 0 && lane == 0) {
+        for (int b = 0; b < boxes.n; ++b)
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.m[boxes.map[b]]) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kGramStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            mbar_init(&accum_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_smem)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (num_kb > 0) {
+        if (warp == 0) {
+            // ===== TMA producer =====
+            if (lane == 0) {
+                const uint32_t stage_tx = (uint32_t)boxes.n * (uint32_t)boxes.rows * 128u;
+                int stage = 0; uint32_t phase = 0;
+                for (int kb = my0; kb < my1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_expect_tx(&full_bar[stage], stage_tx);
+                    uint8_t* tile = smem + stage * kStageBytes;
+                    for (int b = 0; b < boxes.n; ++b)
+                        tma_load_2d(tile + b * boxes.rows * 128, &maps.m[boxes.map[b]], kb * kGramKB, boxes.y[b], &full_bar[stage]);
+                    if (++stage == kGramStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer (single elected lane) =====
+            if (lane == 0) {
+                const uint32_t idesc = make_tf32_idesc(kGramRows, n_mma);
+                int stage = 0; uint32_t phase = 0;
+                for (int kb = my0; kb < my1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tile_addr = smem_u32(smem + stage * kStageBytes);
+#pragma unroll
+                    for (int k = 0; k < kGramKB / 8; ++k) {          // UMMA_K = 8 for tf32 → 32-byte steps inside the swizzle row
+                        const uint64_t desc = make_sw128_kmajor_desc(tile_addr + k * 32);
+                        umma_tf32(tmem_base, desc, desc, idesc, (kb > my0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                  // frees the smem slot once these MMAs retire
+                    if (++stage == kGramStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&accum_bar);                             // accumulator complete
+            }
+        } else {
+            // ===== epilogue: TMEM → registers → fp32 reductions into the global R×R tile =====
+            mbar_wait(&accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+            const int row = q * 32 + lane;
+            for (int c0 = 0; c0 < n_mma; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < R) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < R) atomicAdd(out + row * kGramRows + c0 + j, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128));
+    }
+}
+
+}  // namespace mb
+
+using torch::Tensor;
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        TORCH_CHECK(e == cudaSuccess && q == cudaDriverEntryPointSuccess && p, "cuTensorMapEncodeTiled unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+}  // namespace
+
+// One 2-D fp32 tensor map per source buffer: [rows][row_len] with `row_stride` elements between rows,
+// box = [box_rows][32 floats], 128-byte swizzle.  Returns a CPU byte tensor [nbuf][128].
+Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_stride, int64_t row_len, int64_t box_rows) {
+    TORCH_CHECK((int)base_ptrs.size() <= mb::kMaxMaps, "at most ", mb::kMaxMaps, " source buffers");
+    TORCH_CHECK(box_rows % 8 == 0 && box_rows >= 8 && box_rows <= 128, "box_rows must be a multiple of 8 in [8,128]");
+    TORCH_CHECK(row_stride % 4 == 0, "row stride must be 16-byte aligned");
+    Tensor t = torch::zeros({(int64_t)base_ptrs.size(), (int64_t)sizeof(CUtensorMap)}, torch::kUInt8);
+    auto enc = get_encode();
+    for (size_t i = 0; i < base_ptrs.size(); ++i) {
+        cuuint64_t gdim[2] = {(cuuint64_t)row_len, (cuuint64_t)rows};
+        cuuint64_t gstride[1] = {(cuuint64_t)row_stride * 4};
+        cuuint32_t box[2] = {(cuuint32_t)mb::kGramKB, (cuuint32_t)box_rows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(reinterpret_cast<CUtensorMap*>(t.data_ptr<uint8_t>() + i * sizeof(CUtensorMap)),
+                         CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(base_ptrs[i]), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", (int)r);
+    }
+    return t;
+}
+
+// out[128*128] (+)= Gram of the tile rows assembled from `boxes` over k-blocks [kb0, kb1) (32 floats each).
+void gram_tf32(Tensor maps_cpu, std::vector<int64_t> box_map, std::vector<int64_t> box_y, int64_t box_rows, int64_t kb0,
+               int64_t kb1, int64_t R, Tensor out, bool zero_out, int64_t max_ctas) {
+    c10::cuda::CUDAGuard guard(out.device());
+    TORCH_CHECK(out.numel() == mb::kGramRows * mb::kGramRows && out.dtype() == torch::kFloat32 && out.is_contiguous());
+    TORCH_CHECK(box_map.size() == box_y.size() && (int)box_map.size() <= mb::kMaxBoxes && !box_map.empty());
+    const int rows_total = (int)(box_map.size() * box_rows);
+    TORCH_CHECK(rows_total <= mb::kGramRows, "tile holds at most 128 rows");
+    TORCH_CHECK(R <= rows_total);
+    mb::GramMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    memcpy(&maps, maps_cpu.data_ptr<uint8_t>(), (size_t)maps_cpu.numel());
+    mb::GramBoxes boxes;
+    boxes.n = (int)box_map.size(); boxes.rows = (int)box_rows;
+    for (int b = 0; b < boxes.n; ++b) { boxes.map[b] = (int)box_map[b]; boxes.y[b] = (int)box_y[b]; }
+    const int n_mma = std::max(16, (rows_total + 15) / 16 * 16);
+    auto stream = at::cuda::getCurrentCUDAStream();
+    if (zero_out) cudaMemsetAsync(out.data_ptr<float>(), 0, out.numel() * sizeof(float), stream);
+    if (kb1 <= kb0) return;
+    const int smem = mb::kGramStages * mb::kStageBytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(mb::gram_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    if (max_ctas > 0) sms = std::min<int>(sms, (int)max_ctas);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (kb1 - kb0 + 7) / 8));   // >= 8 k-blocks per CTA
+    mb::gram_tf32_kernel<<<grid, mb::kGramThreads, smem, stream>>>(maps, boxes, (int)kb0, (int)kb1, n_mma, (int)R, out.data_ptr<float>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}

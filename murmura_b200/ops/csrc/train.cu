@@ -1,0 +1,188 @@
+// murmura_b200 — local-training and evaluation kernels (sm_100a).
+//
+// Reference call sites replaced: K8 local SGD step (murmura/core/node.py:74-99 —
+// fresh plain SGD, θ -= lr·g), K14 evaluation accumulators (murmura/core/node.py:134-196,
+// murmura/utils/metrics.py:9-47, one host sync per batch in the reference → none here), the
+// evidential loss (murmura/examples/wearables/models.py:89-179) fused forward+backward, and the
+// Dirichlet epilogue used by EvidentialTrust / DMTT scoring (aggregation/evidential_trust.py:236-281).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include "common.cuh"
+
+namespace mb {
+
+// ---- fused multi-slot SGD: θ -= lr·g ; g = 0 (one launch for a whole slot range) -------------------
+__global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ live, size_t stride, float* __restrict__ grad,
+                                                       size_t gstride, int n4, float lr) {
+    const int v = blockIdx.y;
+    float4* p = reinterpret_cast<float4*>(live + (size_t)v * stride);
+    float4* g = reinterpret_cast<float4*>(grad + (size_t)v * gstride);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 w = p[i];
+        const float4 d = g[i];
+        w.x = fmaf(-lr, d.x, w.x); w.y = fmaf(-lr, d.y, w.y); w.z = fmaf(-lr, d.z, w.z); w.w = fmaf(-lr, d.w, w.w);
+        p[i] = w;
+        g[i] = zero;
+    }
+}
+
+// ---- softmax cross-entropy evaluation: one warp per row, device-side accumulators ----------------
+// stats[0] += Σ CE, stats[1] += #correct, stats[2] += #rows  (rows >= n_valid are padding)
+__global__ void ce_eval_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
+                               const int* __restrict__ n_valid_ptr, int B, int C, float* __restrict__ stats) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_valid = n_valid_ptr ? min(*n_valid_ptr, B) : B;
+    float loss = 0.f, correct = 0.f, rows = 0.f;
+    if (warp < n_valid) {
+        const float* z = logits + (size_t)warp * C;
+        float mx = -INFINITY; int arg = 0;
+        for (int c = lane; c < C; c += 32) { const float x = z[c]; if (x > mx) { mx = x; arg = c; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o); const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+        }
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += __expf(z[c] - mx);
+        se = warp_sum(se);
+        const int t = (int)targets[warp];
+        loss = __logf(se) + mx - z[t];
+        correct = (arg == t) ? 1.f : 0.f;
+        rows = 1.f;
+    }
+    if (lane == 0 && rows != 0.f) { atomicAdd(stats + 0, loss); atomicAdd(stats + 1, correct); atomicAdd(stats + 2, rows); }
+}
+
+// ---- Dirichlet (evidential) evaluation: alpha rows → correct, vacuity, entropy, strength, sq-err ----
+// stats[0] += Σ‖y - α/S‖², [1] += #correct, [2] += #rows, [3] += Σ K/S, [4] += Σ H(α/S), [5] += Σ S
+__global__ void dirichlet_eval_kernel(const float* __restrict__ alpha, const long long* __restrict__ targets,
+                                      const int* __restrict__ n_valid_ptr, int B, int C, float* __restrict__ stats) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_valid = n_valid_ptr ? min(*n_valid_ptr, B) : B;
+    if (warp >= n_valid) return;
+    const float* a = alpha + (size_t)warp * C;
+    float S = 0.f, mx = -INFINITY; int arg = 0;
+    for (int c = lane; c < C; c += 32) { const float x = a[c]; S += x; if (x > mx) { mx = x; arg = c; } }
+    S = warp_sum(S);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o); const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    const int t = (int)targets[warp];
+    float ent = 0.f, sq = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float p = a[c] / S;
+        ent -= p * logf(p + 1e-10f);
+        const float d = ((c == t) ? 1.f : 0.f) - p;
+        sq = fmaf(d, d, sq);
+    }
+    ent = warp_sum(ent); sq = warp_sum(sq);
+    if (lane == 0) {
+        atomicAdd(stats + 0, sq); atomicAdd(stats + 1, arg == t ? 1.f : 0.f); atomicAdd(stats + 2, 1.f);
+        atomicAdd(stats + 3, (float)C / S); atomicAdd(stats + 4, ent); atomicAdd(stats + 5, S);
+    }
+}
+
+// ---- evidential loss, forward + gradient in one pass ----------------------------------------------
+__device__ __forceinline__ float digammaf_pos(float x) {            // x > 0
+    float r = 0.f;
+    while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+    const float f = 1.f / (x * x);
+    return r + logf(x) - 0.5f / x - f * (1.f / 12.f - f * (1.f / 120.f - f * (1.f / 252.f)));
+}
+__device__ __forceinline__ float trigammaf_pos(float x) {           // x > 0
+    float r = 0.f;
+    while (x < 6.f) { r += 1.f / (x * x); x += 1.f; }
+    const float f = 1.f / (x * x);
+    return r + 1.f / x + 0.5f * f + (1.f / x) * f * (1.f / 6.f - f * (1.f / 30.f - f * (1.f / 42.f)));
+}
+
+// loss = mean_b [ Σ_k (y_k - α_k/S)² + λ·KL(Dir(α̃)‖Dir(1)) ],  α̃ = y + (1-y)·α
+// One warp per row; writes dL/dα (already divided by B) and accumulates the mean loss.
+__global__ void evidential_loss_kernel(const float* __restrict__ alpha, const long long* __restrict__ targets, int B, int C,
+                                       float lam, const float* __restrict__ lam_ptr, float* __restrict__ loss_out,
+                                       float* __restrict__ grad_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    if (lam_ptr != nullptr) lam = *lam_ptr;                       // annealing coefficient kept on the device (CUDA-graph friendly)
+    const float* a = alpha + (size_t)warp * C;
+    float* g = grad_out + (size_t)warp * C;
+    const int t = (int)targets[warp];
+    float S = 0.f;
+    for (int c = lane; c < C; c += 32) S += a[c];
+    S = warp_sum(S);
+    const float at = a[t];
+    const float St = S - at + 1.f;                               // Σ α̃
+    float mse = 0.f, dot = 0.f, lg = 0.f, term = 0.f, sum_am1 = 0.f;
+    const float psiSt = digammaf_pos(St);
+    for (int c = lane; c < C; c += 32) {
+        const float p = a[c] / S, y = (c == t) ? 1.f : 0.f, d = p - y;
+        mse = fmaf(d, d, mse); dot = fmaf(d, p, dot);
+        const float at_c = (c == t) ? 1.f : a[c];                // α̃_c
+        lg += lgammaf(at_c);
+        term += (at_c - 1.f) * (digammaf_pos(at_c) - psiSt);
+        sum_am1 += at_c - 1.f;
+    }
+    mse = warp_sum(mse); dot = warp_sum(dot); lg = warp_sum(lg); term = warp_sum(term); sum_am1 = warp_sum(sum_am1);
+    const float kl = lgammaf(St) - lgammaf((float)C) - lg + term;
+    const float invB = 1.f / (float)B, tri_St = trigammaf_pos(St);
+    for (int c = lane; c < C; c += 32) {
+        const float p = a[c] / S, y = (c == t) ? 1.f : 0.f;
+        float gr = (2.f / S) * ((p - y) - dot);                   // d mse / d α_c
+        if (c != t) gr += lam * ((a[c] - 1.f) * trigammaf_pos(a[c]) - tri_St * sum_am1);
+        g[c] = gr * invB;
+    }
+    if (lane == 0) atomicAdd(loss_out, (mse + lam * kl) * invB);
+}
+
+}  // namespace mb
+
+using torch::Tensor;
+static inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
+
+void sgd_step(Tensor live, int64_t stride, Tensor grad, int64_t gstride, int64_t slot0, int64_t nslots, int64_t n, double lr) {
+    if (nslots == 0) return;
+    c10::cuda::CUDAGuard guard(live.device());
+    TORCH_CHECK(n % 4 == 0, "parameter region must be padded to a multiple of 4 floats");
+    const int n4 = (int)(n / 4);
+    dim3 grid(std::max(1, std::min((n4 + 255) / 256, (148 * 8) / (int)std::max<int64_t>(1, nslots))), (unsigned)nslots);
+    mb::sgd_step_kernel<<<grid, 256, 0, cur_stream()>>>(live.data_ptr<float>() + (size_t)slot0 * stride, (size_t)stride,
+                                                         grad.data_ptr<float>() + (size_t)slot0 * gstride, (size_t)gstride, n4, (float)lr);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void ce_eval(Tensor logits, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats) {
+    c10::cuda::CUDAGuard guard(logits.device());
+    TORCH_CHECK(logits.is_contiguous() && logits.dtype() == torch::kFloat32 && targets.dtype() == torch::kInt64);
+    const int B = (int)logits.size(0), C = (int)logits.size(1);
+    if (B == 0) return;
+    mb::ce_eval_kernel<<<(B * 32 + 255) / 256, 256, 0, cur_stream()>>>(logits.data_ptr<float>(), reinterpret_cast<const long long*>(targets.data_ptr<int64_t>()),
+        n_valid.has_value() ? n_valid->data_ptr<int>() : nullptr, B, C, stats.data_ptr<float>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void dirichlet_eval(Tensor alpha, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats) {
+    c10::cuda::CUDAGuard guard(alpha.device());
+    TORCH_CHECK(alpha.is_contiguous() && alpha.dtype() == torch::kFloat32 && targets.dtype() == torch::kInt64);
+    const int B = (int)alpha.size(0), C = (int)alpha.size(1);
+    if (B == 0) return;
+    mb::dirichlet_eval_kernel<<<(B * 32 + 255) / 256, 256, 0, cur_stream()>>>(alpha.data_ptr<float>(), reinterpret_cast<const long long*>(targets.data_ptr<int64_t>()),
+        n_valid.has_value() ? n_valid->data_ptr<int>() : nullptr, B, C, stats.data_ptr<float>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+std::vector<Tensor> evidential_loss_fwd_bwd(Tensor alpha, Tensor targets, double lam, c10::optional<Tensor> lam_t) {
+    c10::cuda::CUDAGuard guard(alpha.device());
+    TORCH_CHECK(alpha.is_contiguous() && alpha.dtype() == torch::kFloat32 && targets.dtype() == torch::kInt64);
+    const int B = (int)alpha.size(0), C = (int)alpha.size(1);
+    Tensor loss = torch::zeros({}, alpha.options());
+    Tensor grad = torch::empty_like(alpha);
+    if (B > 0)
+        mb::evidential_loss_kernel<<<(B * 32 + 255) / 256, 256, 0, cur_stream()>>>(alpha.data_ptr<float>(), reinterpret_cast<const long long*>(targets.data_ptr<int64_t>()),
+            B, C, (float)lam, lam_t.has_value() ? lam_t->data_ptr<float>() : nullptr, loss.data_ptr<float>(), grad.data_ptr<float>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return {loss, grad};
+}

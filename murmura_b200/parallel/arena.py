@@ -1,0 +1,231 @@
+"""Flat parameter arena: layout manifest, node→GPU placement, peer-mapped symmetric region.
+
+Design: every virtual node's whole ``state_dict`` lives in ONE fp32 row
+
+    [ parameters (Pp, padded to 4) | float buffers (Pb) | pad to 256 | int buffers as float (Pi) | pad to 256 ]
+
+so local SGD writes parameters *in place* in the arena and the fused exchange+aggregate kernels see a
+node as ``base + slot*stride``.  Each rank owns one symmetric region (cudaMalloc + cudaIpc, mapped
+into every peer) holding three planes of ``S`` rows — ``live``, ``published[0]``, ``published[1]``
+(double-buffered by round parity ⇒ the reference's Jacobi semantics, ``core/network.py:108,138-139``) —
+followed by the published Count-Sketches and a control page (per-rank epoch flags, timeout mask).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def _ceil(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class Entry:
+    name: str
+    shape: Tuple[int, ...]
+    numel: int
+    offset: int          # element offset inside the row (float region) or inside the int table
+    kind: str            # "param" | "fbuf" | "int"
+    ref_offset: int = -1  # offset in the reference's flatten order (float tensors, state_dict order)
+
+
+@dataclass
+class StateLayout:
+    """Maps ``state_dict`` keys ↔ offsets of one arena row."""
+    entries: List[Entry] = field(default_factory=list)
+    Pp: int = 0           # real parameter elements
+    Pp4: int = 0          # parameter region padded to a multiple of 4 (SGD kernel extent)
+    Pf: int = 0           # end of the float region (params + float buffers), real elements
+    Pf_pad: int = 0       # float region padded to 256 → int tail starts here
+    Pi: int = 0           # int-buffer elements
+    stride: int = 0       # elements per row
+    P_float_real: int = 0  # number of float state elements (reference's "model_dim")
+
+    @classmethod
+    def from_model(cls, model: nn.Module) -> "StateLayout":
+        lay = cls()
+        param_names = {n for n, _ in model.named_parameters()}
+        state = model.state_dict()
+        ref_off = 0
+        ref_offsets: Dict[str, int] = {}
+        for name, t in state.items():
+            if t.is_floating_point():
+                ref_offsets[name] = ref_off
+                ref_off += t.numel()
+        lay.P_float_real = ref_off
+        off = 0
+        for name, t in state.items():
+            if name in param_names:
+                lay.entries.append(Entry(name, tuple(t.shape), t.numel(), off, "param", ref_offsets[name]))
+                off += t.numel()
+        lay.Pp = off
+        lay.Pp4 = _ceil(off, 4)
+        off = lay.Pp4
+        for name, t in state.items():
+            if name not in param_names and t.is_floating_point():
+                lay.entries.append(Entry(name, tuple(t.shape), t.numel(), off, "fbuf", ref_offsets[name]))
+                off += t.numel()
+        lay.Pf = off
+        lay.Pf_pad = _ceil(max(off, 4), 256)
+        ioff = 0
+        for name, t in state.items():
+            if not t.is_floating_point():
+                lay.entries.append(Entry(name, tuple(t.shape), t.numel(), ioff, "int"))
+                ioff += t.numel()
+        lay.Pi = ioff
+        lay.stride = lay.Pf_pad + (_ceil(ioff, 256) if ioff else 0)
+        return lay
+
+    # ---- views ------------------------------------------------------------------------------
+    def float_entries(self) -> List[Entry]:
+        return [e for e in self.entries if e.kind != "int"]
+
+    def int_entries(self) -> List[Entry]:
+        return [e for e in self.entries if e.kind == "int"]
+
+    def row_views(self, row: torch.Tensor, ints: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """state-dict-shaped views of one arena row (+ optional int64 table row)."""
+        out: Dict[str, torch.Tensor] = {}
+        for e in self.entries:
+            if e.kind == "int":
+                if ints is not None:
+                    out[e.name] = ints[e.offset:e.offset + e.numel].view(e.shape)
+            else:
+                out[e.name] = row[e.offset:e.offset + e.numel].view(e.shape)
+        return out
+
+    def ref_permutation(self) -> np.ndarray:
+        """``perm[arena_pos] = reference flatten index`` for real float elements, -1 for padding."""
+        perm = np.full(self.Pf, -1, dtype=np.int64)
+        for e in self.float_entries():
+            perm[e.offset:e.offset + e.numel] = np.arange(e.ref_offset, e.ref_offset + e.numel)
+        return perm
+
+    def bind(self, model: nn.Module, row: torch.Tensor, grad_row: Optional[torch.Tensor], ints: Optional[torch.Tensor]) -> None:
+        """Re-point ``model``'s parameters/buffers at the arena (values are copied in first)."""
+        params = dict(model.named_parameters())
+        modules = dict(model.named_modules())
+        with torch.no_grad():
+            for e in self.entries:
+                if e.kind == "param":
+                    p = params[e.name]
+                    view = row[e.offset:e.offset + e.numel].view(e.shape)
+                    view.copy_(p.detach())
+                    p.data = view
+                    if grad_row is not None:
+                        p.grad = grad_row[e.offset:e.offset + e.numel].view(e.shape)
+                else:
+                    mod_name, _, leaf = e.name.rpartition(".")
+                    mod = modules[mod_name]
+                    old = mod._buffers[leaf]
+                    if e.kind == "fbuf":
+                        view = row[e.offset:e.offset + e.numel].view(e.shape)
+                    else:
+                        view = ints[e.offset:e.offset + e.numel].view(e.shape)
+                    view.copy_(old)
+                    mod._buffers[leaf] = view
+
+
+@dataclass
+class Placement:
+    """Contiguous packing of N nodes onto G ranks (first ``N % G`` ranks host one extra node)."""
+    num_nodes: int
+    world: int
+
+    def __post_init__(self) -> None:
+        base, rem = divmod(self.num_nodes, self.world)
+        self.counts = [base + (1 if r < rem else 0) for r in range(self.world)]
+        self.starts = np.concatenate([[0], np.cumsum(self.counts)]).tolist()
+        self.slots_per_rank = max(self.counts) if self.counts else 0
+        self.rank_of = np.zeros(self.num_nodes, dtype=np.int32)
+        self.slot_of = np.zeros(self.num_nodes, dtype=np.int32)
+        for r in range(self.world):
+            for s in range(self.counts[r]):
+                self.rank_of[self.starts[r] + s] = r
+                self.slot_of[self.starts[r] + s] = s
+
+    def local_nodes(self, rank: int) -> List[int]:
+        return list(range(self.starts[rank], self.starts[rank + 1]))
+
+
+class SymmetricArena:
+    """One rank's peer-mapped region + typed views + device pointer tables for the kernels."""
+
+    CTRL_BYTES = 4096
+
+    def __init__(self, layout: StateLayout, placement: Placement, rank: int, device: torch.device,
+                 sketch_size: int = 0, group=None):
+        from murmura_b200 import ops
+        self.layout, self.placement, self.rank, self.device = layout, placement, rank, device
+        self.world = placement.world
+        S, stride = placement.slots_per_rank, layout.stride
+        self.S = S
+        self.K = sketch_size
+        self.Kpad = _ceil(sketch_size, 32) if sketch_size else 0
+        plane = S * stride * 4
+        self.off_live = 0
+        self.off_pub = plane                               # two planes follow
+        self.off_sketch = self.off_pub + 2 * plane
+        sk_bytes = _ceil(2 * S * self.K * 4, 256)
+        self.off_sketch_q = self.off_sketch + sk_bytes
+        q_bytes = _ceil(2 * S * self.Kpad, 256)
+        self.off_sketch_sc = self.off_sketch_q + q_bytes
+        sc_bytes = _ceil(2 * S * (self.Kpad // 32 if self.Kpad else 0), 256)
+        self.off_ctrl = _ceil(self.off_sketch_sc + sc_bytes, 4096)
+        total = self.off_ctrl + self.CTRL_BYTES
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        self._arena = ops.ext().PeerArena(index, total, rank, self.world)
+        if self.world > 1:
+            import torch.distributed as dist
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, self._arena.ipc_handle(), group=group)
+            self._arena.open_peers([bytes(h) for h in handles])
+            dist.barrier(group=group)
+        a = self._arena
+        self.live = a.view(rank, self.off_live, [S, stride], torch.float32)
+        self.pub = a.view(rank, self.off_pub, [2, S, stride], torch.float32)
+        self.sketch = a.view(rank, self.off_sketch, [2, S, self.K], torch.float32) if self.K else None
+        self.flags = a.view(rank, self.off_ctrl, [16], torch.int32)
+        self.timed_out = a.view(rank, self.off_ctrl + 64, [1], torch.int32)
+        # device pointer tables (int64[G]) handed to kernels as `const T* const*`
+        self.tbl_pub = a.ptr_table(self.off_pub)
+        self.tbl_live = a.ptr_table(self.off_live)
+        self.tbl_sketch = a.ptr_table(self.off_sketch)
+        self.tbl_sketch_q = a.ptr_table(self.off_sketch_q)
+        self.tbl_sketch_sc = a.ptr_table(self.off_sketch_sc)
+        self.tbl_flags = a.ptr_table(self.off_ctrl)
+
+    # pointers -----------------------------------------------------------------------------------
+    def pub_plane_ptr(self, parity: int) -> int:
+        return self._arena.base_ptr(self.rank) + self.off_pub + parity * self.S * self.layout.stride * 4
+
+    def parity_off(self, parity: int) -> int:
+        return parity * self.S * self.layout.stride
+
+    def base_ptr(self, rank: int) -> int:
+        return self._arena.base_ptr(rank)
+
+    def peer_row(self, rank: int, parity: int, slot: int) -> torch.Tensor:
+        """Published row of (rank, slot) as a tensor — local or peer-mapped (read in place over NVLink)."""
+        off = self.off_pub + ((parity * self.S + slot) * self.layout.stride) * 4
+        return self._arena.view(rank, off, [self.layout.stride], torch.float32)
+
+    def sketch_q_ptr(self) -> int:
+        return self._arena.base_ptr(self.rank) + self.off_sketch_q
+
+    def sketch_sc_ptr(self) -> int:
+        return self._arena.base_ptr(self.rank) + self.off_sketch_sc
+
+    def flags_ptr(self) -> int:
+        return self._arena.base_ptr(self.rank) + self.off_ctrl
+
+    def timed_out_ptr(self) -> int:
+        return self._arena.base_ptr(self.rank) + self.off_ctrl + 64
+
+    def close(self) -> None:
+        self._arena.close()

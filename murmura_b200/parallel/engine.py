@@ -1,0 +1,938 @@
+"""B200 engine: one SPMD process per GPU, virtual nodes in a flat peer-mapped arena, fused kernels.
+
+Public surface mirrors the reference orchestrator (``murmura/core/network.py:16-312``):
+``B200Network.from_config(...)``, ``train(rounds, local_epochs, lr, verbose, eval_every) -> history``,
+``get_node_statistics()``; the stdout contract and history schema are shared with the simulation
+backend through :func:`murmura_b200.core.network.record_round`.
+
+One round (per rank; all device work is enqueued without host synchronisation):
+
+1. **local training** of every honest virtual node hosted here — parameters are views into the arena's
+   ``live`` plane, each node's step (gather batch → forward → loss → backward → fused flat SGD kernel)
+   is a CUDA graph replayed ``epochs × batches`` times on one of ``b200.streams`` streams;
+2. **publish** — ``live → published[parity]`` with the Byzantine attack fused in (Philox Gaussian noise /
+   directed-deviation scale), then a release-store of the round epoch into every peer's control page;
+3. **filter** — the aggregator's decision kernels (distances, Gram on tcgen05, Count-Sketch, trust …)
+   wait on the epoch flags *inside the kernel* and read neighbour tiles straight from peer memory;
+4. **weighted_gather** — streams the accepted neighbours' tiles over NVLink and writes ``live`` in place;
+5. **evaluation** (every ``eval_every`` rounds) with device-side accumulators, one small D2H per eval.
+
+NCCL is only used for bootstrap (IPC-handle exchange) and for tiny control tensors (metrics, the
+128×128 Gram partials, DMTT collaborator rows).
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from contextlib import nullcontext
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from murmura_b200.aggregation.balance import decayed_factor
+from murmura_b200.core.network import new_history, record_round
+from murmura_b200.parallel.arena import Placement, StateLayout, SymmetricArena
+from murmura_b200.topology.base import Topology
+
+_STAT_COLS = 8
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def init_distributed() -> Tuple[int, int, int]:
+    """(rank, world, local_rank) — initialises the NCCL group when launched under torchrun."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1:
+        dist = _dist()
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29511")
+            dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo",
+                                    device_id=torch.device("cuda", local_rank) if torch.cuda.is_available() else None)
+    return rank, world, local_rank
+
+
+@dataclass
+class VirtualNode:
+    gid: int
+    slot: int
+    model: nn.Module
+    X: torch.Tensor
+    y: torch.Tensor
+    n: int
+    eb: int                 # effective batch size  min(bs, max(2, n))
+    nb: int                 # batches per epoch (drop_last when n > eb)
+    byzantine: bool = False
+    perm_buf: Optional[torch.Tensor] = None
+    step: Optional[torch.Tensor] = None
+    arange: Optional[torch.Tensor] = None
+    loss_sum: Optional[torch.Tensor] = None
+    train_graph: Any = None
+    eval_graph: Any = None
+    graph_key: Any = None
+
+
+class B200Network:
+    """Blackwell-native counterpart of ``Network`` (same ``train``/``history`` contract)."""
+
+    def __init__(self, config, model_factory: Callable[[], nn.Module], dataset_adapter, aggregator_factory,
+                 device: Optional[torch.device] = None, criterion: Optional[nn.Module] = None, evidential: bool = False):
+        from murmura_b200 import ops
+        from murmura_b200.topology import create_topology
+        from murmura_b200.utils.factories import build_attack, build_mobility_model
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("backend 'b200' needs a CUDA device (use backend: simulation on CPU)")
+        self.ext = ops.ext()                       # fail loudly if the sm_100a extension is missing
+        self.cfg = config
+        self.opt = config.b200
+        self.rank, self.world, local_rank = init_distributed()
+        if self.world > 1:
+            self.device = torch.device("cuda", local_rank)
+        elif device is not None and device.type == "cuda" and device.index is not None:
+            self.device = device
+        else:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        self.is_primary = self.rank == 0
+        self.evidential = evidential
+        self.criterion = criterion
+        self.N = config.topology.num_nodes
+        self.history = new_history()
+        self._apply_math_mode()
+
+        # ---- topology / attack / mobility ----------------------------------------------------
+        t = config.topology
+        self.mobility = build_mobility_model(config)
+        self.topology: Topology = create_topology(t.type, t.num_nodes, p=t.p, k=t.k, seed=t.seed)
+        import contextlib, io
+        with (contextlib.redirect_stdout(io.StringIO()) if not self.is_primary else nullcontext()):
+            self.attack = build_attack(config)
+        self.compromised = set(self.attack.get_compromised_nodes()) if self.attack else set()
+        self.aggregator = aggregator_factory(0)     # hyper-parameters + host-side statistics container
+        self.family = getattr(self.aggregator, "kernel_family", "generic")
+
+        # ---- arena ---------------------------------------------------------------------------
+        self.placement = Placement(self.N, self.world)
+        probe = model_factory()
+        self.layout = StateLayout.from_model(probe)
+        sketch_k = int(getattr(self.aggregator, "sketch_size", 0)) if self.family == "sketchguard" else 0
+        self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k)
+        S, L = self.placement.slots_per_rank, self.layout
+        self.S = S
+        self.live = self.arena.live
+        self.grad = torch.zeros(S, L.Pp4, device=self.device)
+        self.ints = torch.zeros(S, max(L.Pi, 1), dtype=torch.int64, device=self.device)
+        self.local_gids = self.placement.local_nodes(self.rank)
+        self.V = len(self.local_gids)
+
+        # ---- virtual nodes -------------------------------------------------------------------
+        self.nodes: List[VirtualNode] = []
+        bs = config.training.batch_size
+        for slot, gid in enumerate(self.local_gids):
+            torch.manual_seed(config.experiment.seed * 1000003 + gid)       # per-node init stream, rank-layout independent
+            model = model_factory().to(self.device)
+            L.bind(model, self.live[slot], self.grad[slot], self.ints[slot] if L.Pi else None)
+            X, y = dataset_adapter.client_tensors(gid)
+            X = X.to(self.device, non_blocking=True).float().contiguous()
+            y = y.to(self.device, non_blocking=True).long().contiguous()
+            n = int(y.shape[0])
+            eb = min(bs, max(2, n))
+            nb = (n // eb) if n > eb else (1 if n >= 2 else 0)
+            eb = min(eb, n) if n >= 2 else eb
+            self.nodes.append(VirtualNode(gid=gid, slot=slot, model=model, X=X, y=y, n=n, eb=eb, nb=nb,
+                                          byzantine=gid in self.compromised))
+        del probe
+        torch.manual_seed(config.experiment.seed + 7919 * self.rank)
+
+        # ---- attack parameters on the device (fused into publish) ------------------------------
+        spec = self.attack.device_spec() if self.attack is not None and hasattr(self.attack, "device_spec") else None
+        self.attack_spec = spec
+        scale = torch.ones(max(self.V, 1)); noise = torch.zeros(max(self.V, 1))
+        if spec is not None:
+            for vn in self.nodes:
+                if vn.byzantine:
+                    scale[vn.slot] = spec["scale"]; noise[vn.slot] = spec["noise_std"]
+        self.atk_scale = scale.to(self.device); self.atk_noise = noise.to(self.device)
+        self.node_gid = torch.tensor(self.local_gids or [0], dtype=torch.int32, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.custom_attack = self.attack is not None and spec is None and any(vn.byzantine for vn in self.nodes) \
+            and not (hasattr(self.attack, "device_spec"))
+
+        # ---- streams / buffers ---------------------------------------------------------------
+        self.main = torch.cuda.current_stream(self.device)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, self.opt.streams))]
+        self.eval_stats = torch.zeros(max(self.V, 1), _STAT_COLS, device=self.device)
+        self.metrics_host = torch.zeros(self.placement.slots_per_rank * self.world, _STAT_COLS).pin_memory()
+        self.lam_t = torch.zeros((), device=self.device)
+        self.round_idx = 0
+        self.epoch = 0
+        self._lr = None
+        self._edge_cache: Dict[Any, Dict[str, torch.Tensor]] = {}
+        self._stat_log: List[torch.Tensor] = []
+        self._agg_state: Dict[str, torch.Tensor] = {}
+        self.timers: Dict[str, float] = {"train_ms": 0.0, "aggregate_ms": 0.0, "eval_ms": 0.0, "rounds": 0}
+        self.kernel_launches = 0
+        self._dmtt_init()
+        self._sketch_init()
+
+    # =========================================================================================
+    # construction helpers
+    # =========================================================================================
+    @classmethod
+    def from_config(cls, config, model_factory, dataset_adapter, aggregator_factory, device=None, criterion=None,
+                    evidential=False) -> "B200Network":
+        return cls(config, model_factory, dataset_adapter, aggregator_factory, device=device, criterion=criterion,
+                   evidential=evidential)
+
+    def _apply_math_mode(self) -> None:
+        mode = self.opt.compute_dtype
+        torch.backends.cudnn.benchmark = True
+        if mode in ("tf32", "bf16"):
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+        self._autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if mode == "bf16" else nullcontext
+
+    # =========================================================================================
+    # edge tables
+    # =========================================================================================
+    def _edge_table(self, neighbors: List[List[int]], key: Any = None) -> Dict[str, torch.Tensor]:
+        """Device CSR over this rank's destination slots; row = [self, *neighbours]."""
+        if key is not None and key in self._edge_cache:
+            return self._edge_cache[key]
+        pl = self.placement
+        row_ptr = [0]; rk: List[int] = []; sl: List[int] = []; gid: List[int] = []
+        for vn in self.nodes:
+            srcs = [vn.gid] + [j for j in neighbors[vn.gid] if j != vn.gid]
+            if len(srcs) > 128:
+                raise ValueError("degree + 1 > 128 is not supported by the fused kernels")
+            rk += [int(pl.rank_of[j]) for j in srcs]; sl += [int(pl.slot_of[j]) for j in srcs]; gid += srcs
+            row_ptr.append(len(rk))
+        dev = self.device
+        E = max(len(rk), 1)
+        et = {
+            "row_ptr": torch.tensor(row_ptr if self.V else [0, 0], dtype=torch.int32, device=dev),
+            "src_rank": torch.tensor(rk or [0], dtype=torch.int32, device=dev),
+            "src_slot": torch.tensor(sl or [0], dtype=torch.int32, device=dev),
+            "src_gid": torch.tensor(gid or [0], dtype=torch.int32, device=dev),
+            "mask": torch.ones(E, device=dev),
+            "w": torch.zeros(E, device=dev), "w_tail": torch.zeros(E, device=dev),
+            "d2": torch.zeros(E, device=dev), "dist": torch.zeros(E, device=dev),
+            "n2": torch.zeros(max(self.V, 1), device=dev),
+            "stats": torch.zeros(max(self.V, 1), 4, device=dev),
+            "aux": torch.zeros(E, device=dev), "aux2": torch.zeros(E, device=dev), "aux3": torch.zeros(E, device=dev),
+            "host_rows": row_ptr, "host_gid": gid, "host_rank": rk, "host_slot": sl,
+            "max_m": max([row_ptr[i + 1] - row_ptr[i] for i in range(len(row_ptr) - 1)] or [1]),
+        }
+        if key is not None:
+            self._edge_cache[key] = et
+        return et
+
+    def _apply_fault_mask(self, et: Dict[str, torch.Tensor], round_idx: int) -> None:
+        drops = self.opt.fault_drop_edges.get(round_idx) or self.opt.fault_drop_edges.get(str(round_idx))
+        et["mask"].fill_(1.0)
+        if not drops:
+            return
+        dropped = {(int(a), int(b)) for a, b in drops}
+        rows, gids = et["host_rows"], et["host_gid"]
+        mask = torch.ones(len(gids))
+        for vi, vn in enumerate(self.nodes):
+            for e in range(rows[vi] + 1, rows[vi + 1]):
+                if (gids[e], vn.gid) in dropped:
+                    mask[e] = 0.0
+        et["mask"].copy_(mask.to(self.device))
+
+    def _neighbors_for_round(self, r: int) -> Tuple[List[List[int]], Any]:
+        if self.dmtt_on:
+            return self._dmtt_neighbors(r), None
+        if self.mobility is not None:
+            adj = self.mobility.neighbors_at(r)
+            return [adj[i] for i in range(self.N)], None
+        return self.topology.neighbors, "static"
+
+    # =========================================================================================
+    # training
+    # =========================================================================================
+    def _loss(self, out: torch.Tensor, yb: torch.Tensor) -> torch.Tensor:
+        from murmura_b200 import ops
+        from murmura_b200.models.mlp import EvidentialLoss
+        if self.evidential and isinstance(self.criterion, EvidentialLoss):
+            return ops.evidential_loss(out.float(), yb, self.lam_t)
+        if self.criterion is not None and not self.evidential:
+            return self.criterion(out.float(), yb)
+        if self.criterion is not None:
+            return self.criterion(out.float(), yb, epoch=self.round_idx)
+        return F.cross_entropy(out.float(), yb)
+
+    def _train_step(self, vn: VirtualNode, lr: float) -> None:
+        pos = vn.step * vn.eb + vn.arange
+        idx = vn.perm_buf.index_select(0, pos)
+        xb = vn.X.index_select(0, idx); yb = vn.y.index_select(0, idx)
+        with self._autocast():
+            out = vn.model(xb)
+        loss = self._loss(out, yb)
+        loss.backward()
+        self.ext.sgd_step(self.live, self.layout.stride, self.grad, self.layout.Pp4, vn.slot, 1, self.layout.Pp4, lr)
+        vn.step += 1
+        vn.loss_sum += loss.detach()
+
+    def _graphs_ok(self) -> bool:
+        from murmura_b200.models.mlp import EvidentialLoss
+        if not self.opt.cuda_graphs:
+            return False
+        return not (self.evidential and self.criterion is not None and not isinstance(self.criterion, EvidentialLoss))
+
+    def _prepare_training(self, epochs: int, lr: float) -> None:
+        key = (epochs, lr)
+        for vn in self.nodes:
+            if vn.byzantine or vn.nb == 0:
+                continue
+            need = epochs * vn.nb * vn.eb
+            if vn.perm_buf is None or vn.perm_buf.numel() != need:
+                vn.perm_buf = torch.zeros(need, dtype=torch.int64, device=self.device)
+                vn.step = torch.zeros((), dtype=torch.int64, device=self.device)
+                vn.arange = torch.arange(vn.eb, device=self.device)
+                vn.loss_sum = torch.zeros((), device=self.device)
+                vn.train_graph = None
+            if self._graphs_ok() and (vn.train_graph is None or vn.graph_key != key):
+                self._capture_train(vn, lr)
+                vn.graph_key = key
+
+    def _capture_train(self, vn: VirtualNode, lr: float) -> None:
+        snap, snap_i = self.live[vn.slot].clone(), self.ints[vn.slot].clone()
+        rng = torch.cuda.get_rng_state(self.device)
+        vn.model.train()
+        vn.perm_buf.copy_(torch.arange(vn.perm_buf.numel(), device=self.device) % vn.n)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                vn.step.zero_()
+                self._train_step(vn, lr)
+        torch.cuda.current_stream().wait_stream(side)
+        vn.step.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._train_step(vn, lr)
+        vn.train_graph = graph
+        self.live[vn.slot].copy_(snap); self.ints[vn.slot].copy_(snap_i)
+        self.grad[vn.slot].zero_(); vn.step.zero_(); vn.loss_sum.zero_()
+        torch.cuda.set_rng_state(rng, self.device)
+
+    def _fork(self) -> None:
+        ev = torch.cuda.Event(); ev.record(self.main)
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def _join(self) -> None:
+        for s in self.streams:
+            ev = torch.cuda.Event(); ev.record(s); self.main.wait_event(ev)
+
+    def _local_training(self, epochs: int, lr: float) -> None:
+        from murmura_b200.models.mlp import EvidentialLoss
+        if isinstance(self.criterion, EvidentialLoss):
+            self.lam_t.fill_(self.criterion.anneal(self.round_idx))
+        self._fork()
+        for i, vn in enumerate(self.nodes):
+            if vn.byzantine or vn.nb == 0:
+                continue
+            stream = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(stream):
+                take = vn.nb * vn.eb
+                keys = torch.rand(epochs, vn.n, device=self.device)
+                vn.perm_buf.copy_(keys.argsort(dim=1)[:, :take].reshape(-1))
+                vn.step.zero_(); vn.loss_sum.zero_()
+                vn.model.train()
+                for _ in range(epochs * vn.nb):
+                    if vn.train_graph is not None:
+                        vn.train_graph.replay()
+                    else:
+                        self._train_step(vn, lr)
+                self.kernel_launches += epochs * vn.nb
+        self._join()
+
+    # =========================================================================================
+    # publish + aggregation plans
+    # =========================================================================================
+    def _sync_args(self) -> Tuple[int, int, int, float, int]:
+        if self.world == 1:
+            return 0, 1, 0, 0.0, 0
+        return self.arena.flags_ptr(), self.world, self.epoch, float(self.opt.flag_timeout_ms), self.arena.timed_out_ptr()
+
+    def _publish(self, parity: int) -> None:
+        L = self.layout
+        self.epoch += 1
+        if self.custom_attack:
+            self._publish_custom(parity)
+        if self.V == 0:                         # a rank hosting no node still has to raise its epoch flag
+            self.ext.publish(self.live, self.arena.pub_plane_ptr(parity), L.stride, 1, 0, 0, None, self.atk_scale,
+                             self.atk_noise, self.node_gid, 0, 0, self.arena.tbl_flags.data_ptr() if self.world > 1 else 0,
+                             self.world, self.rank, self.epoch, self.ticket)
+            return
+        self.ext.publish(self.live, self.arena.pub_plane_ptr(parity), L.stride, self.V, L.Pf, L.Pf_pad,
+                         self.ints if L.Pi else None, self.atk_scale, self.atk_noise, self.node_gid,
+                         int(self.cfg.experiment.seed), int(self.round_idx),
+                         self.arena.tbl_flags.data_ptr() if self.world > 1 else 0, self.world, self.rank, self.epoch, self.ticket)
+        self.kernel_launches += 1
+        if self.custom_attack:
+            self._publish_custom_fixup(parity)
+
+    def _publish_custom(self, parity: int) -> None:
+        """Arbitrary user ``Attack`` objects (no ``device_spec``): run them on state-dict views."""
+        self._custom_rows = {}
+        for vn in self.nodes:
+            if vn.byzantine:
+                state = {k: v.clone() for k, v in self.layout.row_views(self.live[vn.slot], self.ints[vn.slot]).items()}
+                self._custom_rows[vn.slot] = self.attack.apply_attack(node_id=vn.gid, model_state=state, round_num=self.round_idx)
+
+    def _publish_custom_fixup(self, parity: int) -> None:
+        for slot, state in self._custom_rows.items():
+            row = self.arena.pub[parity, slot]
+            for e in self.layout.float_entries():
+                row[e.offset:e.offset + e.numel].copy_(state[e.name].reshape(-1).to(row.dtype))
+
+    def _gather(self, et, parity: int, renorm: bool, sync: bool = True) -> None:
+        L = self.layout
+        fp, G, ep, to, tp = self._sync_args() if sync else (0, 1, 0, 0.0, 0)
+        self.ext.weighted_gather(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
+                                 et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], et["w"], L.Pf_pad, renorm,
+                                 fp, G, ep, to, tp)
+        self.kernel_launches += 1
+        if L.Pi:
+            self.ext.tail_blend(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
+                                et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], et["w_tail"], L.Pf_pad, self.ints,
+                                tp)
+            self.kernel_launches += 1
+
+    def _edge_dist(self, et, parity: int, length: int) -> None:
+        L = self.layout
+        fp, G, ep, to, tp = self._sync_args()
+        self.ext.edge_distances(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
+                                et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], length, et["d2"], et["n2"],
+                                fp, G, ep, to, tp)
+        self.kernel_launches += 3
+
+    def _et_args(self, et):
+        return (self.V, et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], et["w"], et["w_tail"], et["stats"])
+
+    def _log_stats(self, et) -> None:
+        self._stat_log.append(et["stats"][: self.V].clone())
+
+    # ---- FedAvg ------------------------------------------------------------------------------
+    def _agg_fedavg(self, et, parity: int) -> None:
+        if "fedavg_ready" not in et:
+            self.ext.fedavg_weights(*self._et_args(et)); et["fedavg_ready"] = True
+        self._gather(et, parity, renorm=True)
+
+    # ---- BALANCE -----------------------------------------------------------------------------
+    def _agg_balance(self, et, parity: int) -> None:
+        a = self.aggregator
+        self._edge_dist(et, parity, self.layout.stride)          # all keys: float region + int tail
+        factor = decayed_factor(a.gamma, a.kappa, self.round_idx, a.total_rounds)
+        self.ext.balance_filter(*self._et_args(et), et["d2"], et["n2"], et["dist"], factor, a.alpha, a.min_neighbors,
+                                self._sync_args()[4])
+        self.kernel_launches += 1
+        self._log_stats(et)
+        self._gather(et, parity, renorm=False, sync=False)
+
+    # ---- Sketchguard -------------------------------------------------------------------------
+    def _sketch_init(self) -> None:
+        if self.family != "sketchguard":
+            return
+        from murmura_b200.aggregation.sketchguard import pack_sketch_tables
+        a, L = self.aggregator, self.layout
+        perm = L.ref_permutation()
+        packed_ref = pack_sketch_tables(a.hash_table, a.sign_table)
+        table = np.zeros(_ceil4(L.Pf), dtype=np.uint16)
+        ok = perm >= 0
+        table[: L.Pf][ok] = packed_ref[perm[ok]]
+        self.sk_table = torch.from_numpy(table.view(np.int16)).to(self.device)
+        self.sk_own = torch.zeros(max(self.V, 1), a.sketch_size, device=self.device)
+        self.sk_hist = torch.zeros(max(self.V, 1), 4, device=self.device)
+        self.sk_slots = torch.arange(max(self.V, 1), dtype=torch.int32, device=self.device)
+        self.sk_fp8 = self.opt.sketch_dtype == "fp8"
+
+    def _agg_sketchguard(self, et, parity: int) -> None:
+        a, L, ar = self.aggregator, self.layout, self.arena
+        K = a.sketch_size
+        # sketches of the published rows go into the symmetric region (read by neighbours), sketches of
+        # the live rows stay local; both in one pass each over the data already resident in L2/HBM
+        self.ext.count_sketch(ar.pub_plane_ptr(parity), L.stride, self.sk_slots[: self.V], self.sk_table, L.Pf, K,
+                              ar.sketch[parity, : self.V])
+        self.ext.count_sketch(self.live.data_ptr(), L.stride, self.sk_slots[: self.V], self.sk_table, L.Pf, K,
+                              self.sk_own[: self.V])
+        if self.sk_fp8:
+            self.ext.sketch_quant_mxfp8(ar.sketch[parity, : self.V], ar.sketch_q_ptr() + parity * self.S * ar.Kpad,
+                                        ar.sketch_sc_ptr() + parity * self.S * (ar.Kpad // 32), ar.Kpad)
+        self.kernel_launches += 5
+        if self.world > 1:                              # sketches are written after the publish flag → second epoch
+            self._signal_epoch()
+        factor = decayed_factor(a.gamma, a.kappa, self.round_idx, a.total_rounds)
+        fp, G, ep, to, tp = self._sync_args()
+        self.ext.sketchguard_filter(*self._et_args(et), self.sk_own, ar.tbl_sketch.data_ptr(), ar.tbl_sketch_q.data_ptr(),
+                                    ar.tbl_sketch_sc.data_ptr(), parity * self.S, K, max(ar.Kpad, 32), self.sk_fp8, factor,
+                                    a.alpha, a.min_neighbors, self.sk_hist, et["dist"], fp, G, ep, to, tp)
+        self.kernel_launches += 1
+        self._log_stats(et)
+        self._gather(et, parity, renorm=False, sync=False)
+
+    def _signal_epoch(self) -> None:
+        """Extra release of the epoch counter (zero-length publish) after auxiliary symmetric writes."""
+        L = self.layout
+        self.epoch += 1
+        self.ext.publish(self.live, self.arena.pub_plane_ptr(0), L.stride, 1, 0, 0, None,
+                         self.atk_scale, self.atk_noise, self.node_gid, 0, 0, self.arena.tbl_flags.data_ptr(), self.world,
+                         self.rank, self.epoch, self.ticket)
+        self.kernel_launches += 1
+
+    # ---- Krum --------------------------------------------------------------------------------
+    def _krum_tables(self, et) -> None:
+        if "krum_D" not in et:
+            et["krum_D"] = torch.zeros(max(self.V, 1), 32, 32, device=self.device)
+            et["krum_win"] = torch.zeros(max(self.V, 1), dtype=torch.int32, device=self.device)
+
+    def _gram_plan(self, et) -> Optional[Dict[str, Any]]:
+        """Tile plan for the tcgen05 Gram: rows = live+published planes of every rank."""
+        if self.opt.krum_gram == "fp32":
+            return None
+        if "gram_plan" in et:
+            return et["gram_plan"]
+        S, G, L = self.S, self.world, self.layout
+        box = (S + 7) // 8 * 8
+        plan = None
+        if 2 * G * box <= 128 and et["max_m"] <= 32:
+            row_of_live = lambda r, s: (2 * r) * box + s
+            row_of_pub = lambda r, s: (2 * r + 1) * box + s
+            idx = torch.zeros(max(self.V, 1), 32, dtype=torch.int64)
+            rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
+            for vi, vn in enumerate(self.nodes):
+                for c, e in enumerate(range(rows[vi], rows[vi + 1])):
+                    idx[vi, c] = row_of_live(self.rank, vn.slot) if c == 0 else row_of_pub(rk[e], sl[e])
+            maps = self.ext.gram_make_maps([self.arena.base_ptr(r) for r in range(G)], 3 * S, L.stride, L.Pf_pad, box)
+            nkb = L.Pf_pad // 32
+            lo, hi = nkb * self.rank // G, nkb * (self.rank + 1) // G
+            plan = {"maps": maps, "box": box, "idx": idx.to(self.device), "kb": (lo, hi), "R": 2 * G * box,
+                    "out": torch.zeros(128 * 128, device=self.device)}
+        et["gram_plan"] = plan
+        return plan
+
+    def _agg_krum(self, et, parity: int) -> None:
+        L = self.layout
+        self._krum_tables(et)
+        plan = self._gram_plan(et)
+        fp, G, ep, to, tp = self._sync_args()
+        if plan is not None:
+            if self.world > 1:
+                self._host_wait_epoch()
+            S, box = self.S, plan["box"]
+            box_map, box_y = [], []
+            for r in range(self.world):
+                box_map += [r, r]; box_y += [0, (1 + parity) * S]
+            self.ext.gram_tf32(plan["maps"], box_map, box_y, box, plan["kb"][0], plan["kb"][1], plan["R"], plan["out"], True, 0)
+            self.kernel_launches += 2
+            Gm = plan["out"].view(128, 128)
+            if self.world > 1:
+                _dist().all_reduce(Gm)
+            diag = Gm.diagonal()
+            idx = plan["idx"]
+            D = diag[idx].unsqueeze(2) + diag[idx].unsqueeze(1) - 2.0 * Gm[idx.unsqueeze(2), idx.unsqueeze(1)]
+            et["krum_D"].copy_(D.clamp_min_(0.0))
+        else:
+            self.ext.pairwise_distances(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
+                                        et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], L.Pf_pad, et["krum_D"],
+                                        et["max_m"], fp, G, ep, to, tp)
+            self.kernel_launches += 2
+        self.ext.krum_select(*self._et_args(et), et["krum_D"], int(self.aggregator.num_compromised), et["krum_win"], tp)
+        self.kernel_launches += 1
+        self._log_stats(et)
+        self._gather(et, parity, renorm=False, sync=plan is not None)
+
+    def _host_wait_epoch(self) -> None:
+        """Block the *stream* (not the host) until all ranks published (1-warp spin kernel)."""
+        fp, G, ep, to, tp = self._sync_args()
+        self.ext.wait_epoch(self.live, fp, G, ep, to, tp)
+        self.kernel_launches += 1
+
+    # ---- forward evaluation of foreign weights (UBAR stage 2, EvidentialTrust, DMTT scoring) ----------------
+    def _foreign_state(self, rank: int, parity: int, slot: int, vn: VirtualNode) -> Dict[str, torch.Tensor]:
+        row = self.arena.peer_row(rank, parity, slot)
+        state = self.layout.row_views(row, None)
+        for e in self.layout.int_entries():
+            state[e.name] = self.ints[vn.slot][e.offset:e.offset + e.numel].view(e.shape)
+        return state
+
+    def _forward_with(self, vn: VirtualNode, state: Optional[Dict[str, torch.Tensor]], xb: torch.Tensor) -> torch.Tensor:
+        vn.model.eval()
+        with torch.no_grad(), self._autocast():
+            if state is None:
+                return vn.model(xb).float()
+            return torch.func.functional_call(vn.model, state, (xb,)).float()
+
+    # ---- UBAR --------------------------------------------------------------------------------
+    def _agg_ubar(self, et, parity: int) -> None:
+        a = self.aggregator
+        self._edge_dist(et, parity, self.layout.stride)
+        tp = self._sync_args()[4]
+        cand, rank_t, loss, own_loss = et["aux"], et["aux2"], et["aux3"], et["n2"]
+        self.ext.ubar_stage1(*self._et_args(et), et["d2"], a.rho, a.min_neighbors, cand, rank_t, tp)
+        self.kernel_launches += 1
+        cand_host = cand.cpu()                                       # tiny D2H: which candidates to evaluate
+        rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
+        loss.zero_()
+        for vi, vn in enumerate(self.nodes):
+            if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
+                continue
+            pick = torch.randperm(vn.n, device=self.device)[: vn.eb]
+            xb, yb = vn.X.index_select(0, pick), vn.y.index_select(0, pick)
+            own_loss[vi] = F.cross_entropy(self._forward_with(vn, None, xb), yb)
+            for e in range(rows[vi] + 1, rows[vi + 1]):
+                if cand_host[e] != 0:
+                    loss[e] = F.cross_entropy(self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), xb), yb)
+        self.ext.ubar_stage2(*self._et_args(et), cand, rank_t, loss, own_loss, a.alpha, True)
+        self.kernel_launches += 1
+        self._log_stats(et)
+        self._gather(et, parity, renorm=False, sync=False)
+
+    # ---- EvidentialTrust ----------------------------------------------------------------------
+    def _agg_evidential_trust(self, et, parity: int) -> None:
+        a = self.aggregator
+        if self.world > 1:
+            self._host_wait_epoch()
+        if "ema" not in self._agg_state:
+            self._agg_state["ema"] = torch.zeros(max(self.V, 1), self.N, device=self.device)
+            self._agg_state["ema_valid"] = torch.zeros(max(self.V, 1), self.N, device=self.device)
+        vac, acc, trust = et["aux"], et["aux2"], et["aux3"]
+        rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
+        stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        for vi, vn in enumerate(self.nodes):
+            if vn.n == 0:
+                continue
+            order = torch.randperm(vn.n, device=self.device)
+            nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
+            take = order[: min(vn.n, nbatch * vn.eb)]
+            xb, yb = vn.X.index_select(0, take), vn.y.index_select(0, take)
+            for e in range(rows[vi] + 1, rows[vi + 1]):
+                alpha = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), xb)
+                self.ext.dirichlet_eval(alpha.contiguous(), yb, None, stats[e])
+        cnt = stats[:, 2].clamp_min(1.0)
+        vac.copy_((stats[:, 3] / cnt)[: vac.numel()]); acc.copy_((stats[:, 1] / cnt)[: acc.numel()])
+        self.ext.trust_filter(*self._et_args(et), vac, acc, et["src_gid"], self.N, self._agg_state["ema"],
+                              self._agg_state["ema_valid"], a.accuracy_weight, a.vacuity_threshold, a.trust_momentum,
+                              bool(a.use_adaptive_trust), a.current_threshold(self.round_idx), a.self_weight, trust,
+                              self._sync_args()[4])
+        self.kernel_launches += 2
+        self._log_stats(et)
+        self._gather(et, parity, renorm=False, sync=False)
+
+    # ---- generic (user-defined Aggregator subclasses) -------------------------------------------
+    def _agg_generic(self, et, parity: int) -> None:
+        if self.world > 1:
+            self._host_wait_epoch()
+            torch.cuda.synchronize()
+        rows, rk, sl, gids = et["host_rows"], et["host_rank"], et["host_slot"], et["host_gid"]
+        results = []
+        for vi, vn in enumerate(self.nodes):
+            own = {k: v.clone() for k, v in self.layout.row_views(self.live[vn.slot], self.ints[vn.slot]).items()}
+            nbrs = {}
+            for e in range(rows[vi] + 1, rows[vi + 1]):
+                row = self.arena.peer_row(rk[e], parity, sl[e])
+                st = {k: v.clone() for k, v in self.layout.row_views(row, None).items()}
+                for en in self.layout.int_entries():
+                    st[en.name] = row[self.layout.Pf_pad + en.offset: self.layout.Pf_pad + en.offset + en.numel].round().long().view(en.shape)
+                nbrs[gids[e]] = st
+            results.append(self.aggregator.aggregate(node_id=vn.gid, own_state=own, neighbor_states=nbrs,
+                                                     round_num=self.round_idx, model_template=vn.model, device=self.device,
+                                                     train_loader=None))
+        for vn, st in zip(self.nodes, results):
+            views = self.layout.row_views(self.live[vn.slot], self.ints[vn.slot])
+            for k, v in st.items():
+                views[k].copy_(v.to(views[k].dtype))
+
+    def _aggregate(self, parity: int) -> None:
+        neighbors, key = self._neighbors_for_round(self.round_idx)
+        et = self._edge_table(neighbors, key)
+        if self.opt.fault_drop_edges:
+            self._apply_fault_mask(et, self.round_idx)
+        if self.world > 1:
+            self.arena.timed_out.zero_()
+        self._publish(parity)
+        if self.dmtt_on:
+            self._dmtt_score_and_update(et, parity)
+        plan = getattr(self, f"_agg_{self.family}", self._agg_generic)
+        plan(et, parity)
+
+    # =========================================================================================
+    # evaluation
+    # =========================================================================================
+    def _eval_node(self, vn: VirtualNode) -> None:
+        stats = self.eval_stats[vn.slot]
+        stats.zero_()
+        vn.model.eval()
+        EB = max(1, self.opt.eval_batch)
+        with torch.no_grad():
+            for a in range(0, vn.n, EB):
+                xb, yb = vn.X[a:a + EB], vn.y[a:a + EB]
+                with self._autocast():
+                    out = vn.model(xb).float().contiguous()
+                if self.evidential:
+                    self.ext.dirichlet_eval(out, yb, None, stats)
+                else:
+                    self.ext.ce_eval(out, yb, None, stats)
+
+    def _evaluate(self) -> List[Dict[str, Any]]:
+        self._fork()
+        for i, vn in enumerate(self.nodes):
+            stream = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(stream):
+                if self.opt.cuda_graphs:
+                    if vn.eval_graph is None:
+                        self._capture_eval(vn)
+                    vn.eval_graph.replay()
+                else:
+                    self._eval_node(vn)
+                self.kernel_launches += 1
+        self._join()
+        S = self.placement.slots_per_rank
+        local = torch.zeros(S, _STAT_COLS, device=self.device)
+        local[: self.V] = self.eval_stats[: self.V]
+        if self.world > 1:
+            full = torch.zeros(S * self.world, _STAT_COLS, device=self.device)
+            _dist().all_gather_into_tensor(full, local)
+        else:
+            full = local
+        self.metrics_host[: full.shape[0]].copy_(full, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the one host sync per evaluated round
+        host = self.metrics_host.numpy()
+        per_node = []
+        for gid in range(self.N):
+            r, s = int(self.placement.rank_of[gid]), int(self.placement.slot_of[gid])
+            row = host[r * S + s]
+            total = max(float(row[2]), 1.0)
+            m = {"node_id": gid, "accuracy": float(row[1]) / total, "loss": float(row[0]) / total,
+                 "correct": int(row[1]), "total": int(row[2])}
+            if self.evidential:
+                m.update(vacuity=float(row[3]) / total, entropy=float(row[4]) / total, strength=float(row[5]) / total)
+            per_node.append(m)
+        return per_node
+
+    def _capture_eval(self, vn: VirtualNode) -> None:
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._eval_node(vn)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._eval_node(vn)
+        vn.eval_graph = g
+
+    # =========================================================================================
+    # DMTT (dynamic topology + trust) on the device
+    # =========================================================================================
+    def _dmtt_init(self) -> None:
+        self.dmtt_on = self.cfg.dmtt is not None and self.mobility is not None
+        if self.mobility is None:
+            return
+        R = max(int(self.cfg.experiment.rounds), 1)
+        self.pos_dev = torch.from_numpy(self.mobility.positions_tensor(R + 1)).to(self.device)
+        self.adj_dev = torch.zeros(self.N, self.N, dtype=torch.uint8, device=self.device)
+        if not self.dmtt_on:
+            return
+        N, V = self.N, max(self.V, 1)
+        liar = torch.zeros(N, dtype=torch.uint8)
+        if self.attack is not None and hasattr(self.attack, "get_false_claims"):
+            for i in self.compromised:
+                liar[i] = 1
+        self.is_liar = liar.to(self.device)
+        self.claims_dev = torch.zeros(N, N, dtype=torch.uint8, device=self.device)
+        self.collab = None                                    # [N,N] uint8, C^{t-1}
+        self.c_hat = torch.full((V, N), 0.5, device=self.device)
+        self.t_alpha = torch.ones(V, N, device=self.device); self.t_beta = torch.ones(V, N, device=self.device)
+        self.next_collab = torch.zeros(V, N, dtype=torch.uint8, device=self.device)
+        self.q_out = torch.zeros(V, N, device=self.device)
+
+    def _adjacency(self, r: int) -> torch.Tensor:
+        m = self.cfg.mobility
+        self.ext.mobility_adjacency(self.pos_dev, min(r, self.pos_dev.shape[0] - 1), m.area_size, m.comm_range,
+                                    bool(m.ensure_connected), self.adj_dev)
+        self.kernel_launches += 1
+        return self.adj_dev
+
+    def _dmtt_neighbors(self, r: int) -> List[List[int]]:
+        adj = self._adjacency(r)
+        self.ext.liar_claims(adj, self.is_liar, self.claims_dev)
+        if self.collab is None:                              # round 0: C_i = G^0 neighbours
+            self.collab = adj.clone()
+        c = self.collab.cpu().numpy().astype(bool)           # N×N bytes D2H: next round's directed edge list
+        self._received = c & c.T                             # j's state reaches i iff i∈C_j and j∈C_i (i only accepts expected senders)
+        return [np.flatnonzero(self._received[i]).tolist() for i in range(self.N)]
+
+    def _dmtt_score_and_update(self, et, parity: int) -> None:
+        d, N = self.cfg.dmtt, self.N
+        if self.world > 1:
+            self._host_wait_epoch()
+        V = max(self.V, 1)
+        score = torch.zeros(V, N, device=self.device); valid = torch.zeros(V, N, dtype=torch.uint8, device=self.device)
+        received = torch.zeros(V, N, dtype=torch.uint8, device=self.device)
+        rows, rk, sl, gids = et["host_rows"], et["host_rank"], et["host_slot"], et["host_gid"]
+        stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        for vi, vn in enumerate(self.nodes):
+            for e in range(rows[vi] + 1, rows[vi + 1]):
+                out = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), vn.X)
+                if self.evidential:
+                    self.ext.dirichlet_eval(out.contiguous(), vn.y, None, stats[e])
+                else:
+                    self.ext.ce_eval(out.contiguous(), vn.y, None, stats[e])
+        cnt = stats[:, 2].clamp_min(1.0)
+        acc_e = stats[:, 1] / cnt
+        u_e = stats[:, 3] / cnt if self.evidential else torch.zeros_like(acc_e)
+        s_e = (1.0 - u_e) * (d.w_a * acc_e + (1.0 - d.w_a))
+        s_e = torch.where(u_e > d.tau_u, s_e * torch.exp(-(u_e - d.tau_u)), s_e).clamp_min(0.0)
+        ev_i = [vi for vi in range(self.V) for _ in range(rows[vi] + 1, rows[vi + 1])]
+        ee_i = [e for vi in range(self.V) for e in range(rows[vi] + 1, rows[vi + 1])]
+        if ee_i:
+            vi_t = torch.tensor(ev_i, device=self.device); e_t = torch.tensor(ee_i, device=self.device)
+            g_t = et["src_gid"].long().index_select(0, e_t)
+            score[vi_t, g_t] = s_e.index_select(0, e_t); valid[vi_t, g_t] = 1; received[vi_t, g_t] = 1
+        node0 = self.local_gids[0] if self.local_gids else 0
+        self.ext.dmtt_update(self.adj_dev, self.claims_dev, self.collab, received, score, valid, self.c_hat, self.t_alpha,
+                             self.t_beta, self.next_collab, self.q_out, d.rho, d.lambda_forget, d.w_d, d.w_x, d.tau_U, d.eta,
+                             d.lambda1, d.lambda2, d.lambda3, int(d.budget_B), int(node0))
+        self.kernel_launches += 1
+        S = self.placement.slots_per_rank
+        local = torch.zeros(S, N, dtype=torch.uint8, device=self.device)
+        local[: self.V] = self.next_collab[: self.V]
+        if self.world > 1:
+            full = torch.zeros(S * self.world, N, dtype=torch.uint8, device=self.device)
+            _dist().all_gather_into_tensor(full, local)
+        else:
+            full = local
+        rows_idx = torch.tensor([int(self.placement.rank_of[g]) * S + int(self.placement.slot_of[g]) for g in range(N)],
+                                device=self.device)
+        self.collab = full.index_select(0, rows_idx).contiguous()
+
+    # =========================================================================================
+    # round loop
+    # =========================================================================================
+    def train(self, rounds: int, local_epochs: int = 1, lr: float = 0.01, verbose: bool = False,
+              eval_every: int = 1) -> Dict[str, List[Any]]:
+        verbose = verbose and self.is_primary
+        self._prepare_training(local_epochs, lr)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        total_rounds = self.round_idx + rounds
+        for _ in range(rounds):
+            r = self.round_idx
+            if verbose:
+                print(f"\n=== Round {r + 1}/{total_rounds} ===")
+            prof = self.opt.profile
+            if prof:
+                ev[0].record()
+            self._local_training(local_epochs, lr)
+            if prof:
+                ev[1].record()
+            self._aggregate(parity=r & 1)
+            if prof:
+                ev[2].record()
+            if (r + 1) % eval_every == 0:
+                per_node = self._evaluate()
+                record_round(self.history, r + 1, per_node, self.compromised if self.attack else None, verbose)
+            if prof:
+                ev[3].record(); torch.cuda.synchronize()
+                self.timers["train_ms"] += ev[0].elapsed_time(ev[1]); self.timers["aggregate_ms"] += ev[1].elapsed_time(ev[2])
+                self.timers["eval_ms"] += ev[2].elapsed_time(ev[3])
+            self.timers["rounds"] += 1
+            self.round_idx += 1
+            if self.opt.checkpoint_every and self.round_idx % self.opt.checkpoint_every == 0:
+                self.save_checkpoint(os.path.join(self.opt.checkpoint_dir, f"round_{self.round_idx:05d}"))
+        return self.history
+
+    # =========================================================================================
+    # statistics / checkpoint / teardown
+    # =========================================================================================
+    def get_node_statistics(self) -> Dict[int, Dict[str, Any]]:
+        out: Dict[int, Dict[str, Any]] = {}
+        log = torch.stack(self._stat_log).cpu().numpy() if self._stat_log else np.zeros((0, max(self.V, 1), 4))
+        for vi, vn in enumerate(self.nodes):
+            st: Dict[str, Any] = {"total_rounds_processed": int(log.shape[0])}
+            if log.shape[0]:
+                acc, ev_ = log[:, vi, 0], np.maximum(log[:, vi, 1], 1.0)
+                if self.family in ("balance", "sketchguard", "evidential_trust"):
+                    st["mean_acceptance_rate"] = float(np.mean(acc / ev_)); st["current_threshold"] = float(log[-1, vi, 2])
+                if self.family == "ubar":
+                    st["stage1_mean_acceptance_rate"] = float(np.mean(acc / ev_))
+                    st["stage2_mean_acceptance_rate"] = float(np.mean(log[:, vi, 2] / np.maximum(log[:, vi, 3], 1.0)))
+                if self.family == "krum":
+                    st["winner_history"] = log[:, vi, 0].astype(int).tolist()
+            for k in ("train_ms", "aggregate_ms", "eval_ms"):
+                st[k] = self.timers[k]
+            out[vn.gid] = st
+        return out
+
+    def perf_summary(self) -> str:
+        t = self.timers
+        if not t["rounds"] or not self.opt.profile:
+            return f"{int(t['rounds'])} rounds on {self.world} GPU(s); set b200.profile: true for the per-phase split"
+        r = t["rounds"]
+        return (f"train {t['train_ms'] / r:.2f} ms  aggregate {t['aggregate_ms'] / r:.3f} ms  eval {t['eval_ms'] / r:.2f} ms "
+                f"per round ({self.world} GPU(s))")
+
+    def state_dict_of(self, gid: int) -> Dict[str, torch.Tensor]:
+        vn = next(v for v in self.nodes if v.gid == gid)
+        return {k: v.detach().clone() for k, v in self.layout.row_views(self.live[vn.slot], self.ints[vn.slot]).items()}
+
+    def save_checkpoint(self, path: str) -> None:
+        """Flat-arena checkpoint: live plane, int table, RNG, trust state, round index."""
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        blob = {"round_idx": self.round_idx, "epoch": self.epoch, "live": self.live[: self.V].cpu(), "ints": self.ints.cpu(),
+                "rng": torch.cuda.get_rng_state(self.device), "history": self.history, "local_gids": self.local_gids,
+                "agg_state": {k: v.cpu() for k, v in self._agg_state.items()}}
+        if self.dmtt_on:
+            blob["dmtt"] = {"c_hat": self.c_hat.cpu(), "alpha": self.t_alpha.cpu(), "beta": self.t_beta.cpu(),
+                            "collab": None if self.collab is None else self.collab.cpu()}
+        if self.family == "sketchguard":
+            blob["sk_hist"] = self.sk_hist.cpu()
+        torch.save(blob, f"{path}.rank{self.rank}.pt")
+
+    def load_checkpoint(self, path: str) -> None:
+        blob = torch.load(f"{path}.rank{self.rank}.pt", map_location="cpu", weights_only=False)
+        if blob["local_gids"] != self.local_gids:
+            raise ValueError("checkpoint was written with a different node placement")
+        self.round_idx, self.history = blob["round_idx"], blob["history"]
+        self.live[: self.V].copy_(blob["live"]); self.ints.copy_(blob["ints"])
+        torch.cuda.set_rng_state(blob["rng"], self.device)
+        for k, v in blob.get("agg_state", {}).items():
+            self._agg_state[k] = v.to(self.device)
+        if self.dmtt_on and "dmtt" in blob:
+            d = blob["dmtt"]
+            self.c_hat.copy_(d["c_hat"]); self.t_alpha.copy_(d["alpha"]); self.t_beta.copy_(d["beta"])
+            self.collab = None if d["collab"] is None else d["collab"].to(self.device)
+        if self.family == "sketchguard" and "sk_hist" in blob:
+            self.sk_hist.copy_(blob["sk_hist"])
+        if self.world > 1:      # epochs must stay monotone across the job; re-align on the max
+            t = torch.tensor([max(self.epoch, blob["epoch"])], device=self.device)
+            _dist().all_reduce(t, op=_dist().ReduceOp.MAX)
+            self.epoch = int(t.item())
+
+    def close(self) -> None:
+        torch.cuda.synchronize()
+        for vn in self.nodes:
+            vn.train_graph = None; vn.eval_graph = None
+        if self.world > 1:
+            _dist().barrier()
+        self.arena.close()
+
+
+def _ceil4(x: int) -> int:
+    return (x + 3) // 4 * 4

@@ -1,0 +1,139 @@
+import json
+
+import numpy as np
+import pytest
+import torch
+import yaml
+from pydantic import ValidationError
+
+from murmura_b200.config import Config, load_config, save_config
+from murmura_b200.data import (DatasetAdapter, SyntheticAdapter, combine_partitions_with_dirichlet, dirichlet_partition,
+                               iid_partition, natural_partition)
+
+
+def _base():
+    return {"experiment": {"name": "t"}, "topology": {"type": "ring", "num_nodes": 3}, "aggregation": {"algorithm": "fedavg"},
+            "training": {}, "data": {"adapter": "synthetic.mnist"}, "model": {"factory": "models.mlp"}}
+
+
+def test_schema_defaults_and_rejects():
+    c = Config(**_base())
+    assert c.experiment.seed == 42 and c.experiment.rounds == 20 and c.topology.seed == 12345
+    assert c.training.batch_size == 64 and c.training.lr == 0.01 and c.backend == "simulation"
+    assert c.distributed.round_duration_s == 60.0 and c.attack.enabled is False and c.mobility is None
+    assert c.b200.transport == "p2p"
+    with pytest.raises(ValidationError):
+        Config(**{**_base(), "bogus": 1})                                  # unknown top-level key
+    ok = _base(); ok["topology"]["whatever"] = 3; Config(**ok)              # unknown sub-key ignored
+    bad = _base(); bad["aggregation"] = {"algorithm": "median"}
+    with pytest.raises(ValidationError):
+        Config(**bad)
+    c2 = Config(**{**_base(), "backend": "b200", "dmtt": {}, "mobility": {"comm_range": 40}})
+    assert c2.dmtt.budget_B == 5 and c2.mobility.comm_range == 40 and c2.dmtt.lambda4 == 0.1
+
+
+def test_loader_roundtrip(tmp_path):
+    c = Config(**_base())
+    for name in ("a.yaml", "b.yml", "c.json"):
+        p = tmp_path / name
+        save_config(c, p)
+        assert load_config(p).model_dump() == c.model_dump()
+    with pytest.raises(ValueError):
+        save_config(c, tmp_path / "x.toml")
+    with pytest.raises(FileNotFoundError):
+        load_config(tmp_path / "missing.yaml")
+    (tmp_path / "d.txt").write_text("x")
+    with pytest.raises(ValueError):
+        load_config(tmp_path / "d.txt")
+
+
+def test_bundled_configs_load():
+    import glob, os
+    root = os.path.join(os.path.dirname(os.path.dirname(__file__)), "murmura_b200", "examples", "configs")
+    files = glob.glob(os.path.join(root, "*.yaml"))
+    assert len(files) >= 8
+    for f in files:
+        load_config(f)
+
+
+def test_dirichlet_partition_properties():
+    labels = np.repeat(np.arange(6), 100)
+    parts = dirichlet_partition(labels, 5, alpha=0.1, seed=7)
+    flat = sorted(i for p in parts for i in p)
+    assert flat == list(range(600))                        # exact cover
+    assert parts == dirichlet_partition(labels, 5, alpha=0.1, seed=7)
+    assert all(len(p) >= 1 for p in parts)
+    skew = [np.bincount(labels[p], minlength=6).max() / max(len(p), 1) for p in parts]
+    assert np.mean(skew) > 0.4                             # alpha=0.1 is strongly non-IID
+
+
+def test_min_samples_rebalance():
+    labels = np.zeros(40, dtype=int)
+    parts = dirichlet_partition(labels, 8, alpha=0.01, min_samples_per_client=3, seed=0)
+    assert all(len(p) >= 3 for p in parts) and sum(map(len, parts)) == 40
+
+
+def test_iid_natural_combine():
+    parts = iid_partition(103, 4, seed=1)
+    assert sorted(map(len, parts)) == [25, 26, 26, 26] and sorted(i for p in parts for i in p) == list(range(103))
+    ids = np.array([5, 5, 2, 9, 2, 9, 9])
+    nat, k = natural_partition(ids)
+    assert k == 3 and nat == [[2, 4], [0, 1], [3, 5, 6]]
+    nat2, k2 = natural_partition(ids, num_clients=2)
+    assert k2 == 2 and nat2 == [[2, 4], [0, 1]]
+    labels = np.array([0, 1, 0, 1, 0, 1, 0])
+    comb = combine_partitions_with_dirichlet(nat, labels, 2, alpha=1.0, seed=3)
+    assert sorted(i for p in comb for i in p) == list(range(7))
+
+
+def test_adapter_and_synthetic():
+    ad = SyntheticAdapter(name="cifar10", num_nodes=4, samples_per_node=20, seed=1)
+    assert ad.get_num_clients() == 4 and sum(len(p) for p in ad.get_client_partitions()) == 80
+    x, y = ad.get_client_data(0)[0]
+    assert x.shape == (3, 32, 32)
+    X, Y = ad.client_tensors(1)
+    assert X.shape[0] == len(ad.get_client_partitions()[1]) and Y.dtype == torch.long
+    with pytest.raises(ValueError):
+        ad.get_client_data(9)
+    a2 = SyntheticAdapter(name="cifar10", num_nodes=4, samples_per_node=20, seed=1)
+    assert torch.equal(a2.dataset.tensors[0], ad.dataset.tensors[0])
+    with pytest.raises(ValueError):
+        SyntheticAdapter(name="nope")
+    generic = DatasetAdapter([(torch.zeros(2), 1), (torch.ones(2), 0)], [[0], [1]])
+    X, Y = generic.client_tensors(1)
+    assert X.tolist() == [[1.0, 1.0]] and Y.tolist() == [0]
+
+
+def test_wearables_window_helper_and_synthetic_route():
+    from murmura_b200.examples.wearables.datasets import majority_windows
+    feats = np.arange(20, dtype=np.float32).reshape(10, 2)
+    acts = np.array([1, 1, 1, 2, 2, 2, 2, 3, 3, 3])
+    w, l = majority_windows(feats, acts, 4, 2, {1: 0, 2: 1})
+    assert w.shape == (3, 8) and l.tolist() == [0, 1, 1][: len(l)]
+    np.testing.assert_array_equal(w[0], feats[0:4].ravel())
+    from murmura_b200.examples.wearables import load_wearable_adapter, get_wearable_dataset_info
+    ad = load_wearable_adapter("uci_har", "synthetic", num_nodes=3, samples_per_node=10)
+    assert ad.client_tensors(0)[0].shape[1] == 561
+    assert get_wearable_dataset_info("PPG-DaLiA")["num_classes"] == 7
+    with pytest.raises(ValueError):
+        get_wearable_dataset_info("nope")
+
+
+def test_leaf_partitions_and_json_loader(tmp_path):
+    from murmura_b200.examples.leaf.datasets import LEAFFEMNISTDataset, create_leaf_client_partitions
+    for split, k in (("train", 3), ("test", 1)):
+        d = tmp_path / split; d.mkdir()
+        users = [f"u{i}" for i in range(5)]
+        blob = {"users": users, "num_samples": [k + i for i in range(5)],
+                "user_data": {u: {"x": [[0.5] * 784] * (k + i), "y": [i] * (k + i)} for i, u in enumerate(users)}}
+        (d / "all.json").write_text(json.dumps(blob))
+    tr, te = LEAFFEMNISTDataset(str(tmp_path), "train"), LEAFFEMNISTDataset(str(tmp_path), "test")
+    assert len(tr) == 3 + 4 + 5 + 6 + 7 and tr[0][0].shape == (1, 28, 28)
+    a, b = create_leaf_client_partitions(tr, te, num_nodes=2, seed=42)
+    assert sorted(i for p in a for i in p) == list(range(len(tr))) and sorted(i for p in b for i in p) == list(range(len(te)))
+    assert create_leaf_client_partitions(tr, te, 2, 42)[0] == a
+    from murmura_b200.examples.leaf import load_leaf_adapter
+    ad = load_leaf_adapter("femnist", data_path=str(tmp_path), num_nodes=2, seed=42, max_samples=4)
+    assert all(len(p) <= 4 for p in ad.get_client_partitions())
+    syn = load_leaf_adapter("femnist", data_path="synthetic", num_nodes=2, samples_per_node=8)
+    assert syn.client_tensors(0)[0].shape[1:] == (1, 28, 28)

@@ -1,0 +1,193 @@
+"""End-to-end CPU tests: simulation backend, stdout contract, CLI, ZeroMQ backend, DMTT state."""
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+from typer.testing import CliRunner
+
+from murmura_b200 import Network, create_topology
+from murmura_b200.config import Config, load_config
+from murmura_b200.config.schema import DMTTConfig
+from murmura_b200.dmtt import DMTTNodeState
+from murmura_b200.dmtt.node_process import verify_claim
+from murmura_b200.utils.factories import (build_aggregator_factory, build_attack, build_criterion, build_dataset_adapter,
+                                          build_mobility_model, build_model_factory)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(ROOT, "murmura_b200", "examples", "configs")
+
+
+def _cfg(**over):
+    base = {"experiment": {"name": "t", "rounds": 2, "seed": 1}, "topology": {"type": "ring", "num_nodes": 4},
+            "aggregation": {"algorithm": "fedavg"}, "training": {"batch_size": 16, "lr": 0.05},
+            "data": {"adapter": "synthetic.mnist", "params": {"samples_per_node": 48, "partition_method": "iid"}},
+            "model": {"factory": "models.mlp", "params": {"hidden_dims": [16]}}}
+    base.update(over)
+    return Config(**base)
+
+
+def _build(cfg):
+    adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
+    crit, evid = build_criterion(cfg)
+    return Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf, torch.device("cpu")),
+                               device=torch.device("cpu"), criterion=crit, evidential=evid)
+
+
+def test_simple_programmatic_example(capsys):
+    from murmura_b200.examples.simple_programmatic import main
+    hist = main(rounds=3)
+    out = capsys.readouterr().out
+    assert len(hist["round"]) == 3 and hist["mean_accuracy"][-1] > 0.6
+    assert re.search(r"Round 3: Mean Accuracy = \d\.\d{4} ± \d\.\d{4}", out)
+    assert "=== Round 1/3 ===" in out
+
+
+def test_two_node_ring_fedavg_nodes_identical():
+    torch.manual_seed(0)
+    net = _build(_cfg(topology={"type": "ring", "num_nodes": 2}))
+    net.train(rounds=1, lr=0.05)
+    a, b = net.nodes[0].get_state(), net.nodes[1].get_state()
+    assert all(torch.allclose(a[k], b[k]) for k in a)              # each averages {own, other}
+    with pytest.raises(ValueError):
+        Network(net.nodes, create_topology("ring", 3))
+
+
+def test_attack_history_and_contract(capsys):
+    torch.manual_seed(0)
+    cfg = _cfg(attack={"enabled": True, "type": "gaussian", "percentage": 0.25, "params": {"noise_std": 1.0}},
+               aggregation={"algorithm": "balance", "params": {"gamma": 0.5}})
+    net = _build(cfg)
+    hist = net.train(rounds=2, verbose=True, eval_every=1)
+    out = capsys.readouterr().out
+    assert len(hist["honest_accuracy"]) == 2 and len(hist["compromised_accuracy"]) == 2
+    assert re.search(r"  Honest: \d\.\d{4}, Compromised: \d\.\d{4}", out)
+    stats = net.get_node_statistics()
+    assert set(stats) == {0, 1, 2, 3} and "mean_acceptance_rate" in stats[0]
+    byz = next(iter(net.attack.get_compromised_nodes()))
+    assert net.attack.is_compromised(byz)
+    h2 = _build(cfg).train(rounds=2, eval_every=2)
+    assert h2["round"] == [2]
+
+
+def test_evidential_pipeline_and_uncertainty_line(capsys):
+    torch.manual_seed(0)
+    cfg = _cfg(model={"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6, "hidden_dims": [16]}},
+               data={"adapter": "wearables.uci_har", "params": {"data_path": "synthetic", "samples_per_node": 40}},
+               aggregation={"algorithm": "evidential_trust", "params": {"trust_threshold": 0.1}})
+    crit, evid = build_criterion(cfg)
+    assert evid and crit.annealing_epochs == 1 and crit.lambda_weight == 0.1
+    hist = _build(cfg).train(rounds=2, verbose=True)
+    out = capsys.readouterr().out
+    assert len(hist["mean_vacuity"]) == 2
+    assert re.search(r"  Uncertainty: Vacuity=\d+\.\d{4}, Entropy=\d+\.\d{4}, Strength=\d+\.\d{2}", out)
+
+
+@pytest.mark.parametrize("algo,params", [("krum", {"num_compromised": 1}), ("sketchguard", {"sketch_size": 64}),
+                                         ("ubar", {"rho": 0.5}), ("balance", {})])
+def test_all_aggregators_run(algo, params):
+    torch.manual_seed(0)
+    cfg = _cfg(topology={"type": "fully", "num_nodes": 5}, aggregation={"algorithm": algo, "params": params},
+               attack={"enabled": True, "type": "directed_deviation", "percentage": 0.2})
+    hist = _build(cfg).train(rounds=1)
+    assert 0.0 <= hist["mean_accuracy"][0] <= 1.0
+
+
+def test_factories_misc():
+    cfg = _cfg(attack={"enabled": True, "type": "topology_liar", "percentage": 0.5, "params": {"model_attack_type": "gaussian"}},
+               mobility={"comm_range": 50}, dmtt={})
+    atk = build_attack(cfg)
+    assert hasattr(atk, "get_false_claims") and atk._model_attack is not None
+    assert build_mobility_model(cfg).comm_range == 50 and build_mobility_model(_cfg()) is None
+    assert build_attack(_cfg()) is None
+    cfg2 = _cfg(model={"factory": "murmura.models.mlp", "params": {"hidden_dims": [4]}})        # reference-style dotted path
+    assert build_model_factory(cfg2)().net[0].out_features == 4
+    sk = _cfg(aggregation={"algorithm": "sketchguard"})
+    agg = build_aggregator_factory(sk, build_model_factory(sk))(0)
+    assert agg.model_dim == 784 * 16 + 16 + 16 * 10 + 10 and agg.total_rounds == 2
+
+
+def test_cli(tmp_path):
+    from murmura_b200.cli import app
+    runner = CliRunner()
+    res = runner.invoke(app, ["list-components", "aggregators"])
+    assert res.exit_code == 0 and "evidential_trust" in res.stdout
+    assert "b200" in runner.invoke(app, ["list-components", "backends"]).stdout
+    assert "Unknown component type" in runner.invoke(app, ["list-components", "nope"]).stdout
+    res = runner.invoke(app, ["run", os.path.join(CFG, "basic_fedavg.yaml"), "--device", "cpu", "--quiet"])
+    assert res.exit_code == 0 and "Training complete" in res.stdout and "Training Results" in res.stdout
+    bad = tmp_path / "bad.yaml"; bad.write_text("experiment: {name: x}\n")
+    res = runner.invoke(app, ["run", str(bad)])
+    assert res.exit_code == 1 and "Error:" in res.stdout
+
+
+def test_dmtt_state_math():
+    s = DMTTNodeState(0, DMTTConfig(), num_nodes=4)
+    assert s.link_reliability(2) == 0.5 and s.topo_trust(2) == pytest.approx(0.5)      # U=sqrt(1/12)<tau_U
+    s.update_link_reliability(2, True); assert s.link_reliability(2) == pytest.approx(0.55)
+    s.update_link_reliability(2, False); assert s.link_reliability(2) == pytest.approx(0.495)
+    s.update_trust(1, d=3, x=0); a, b = 0.9 + 3, 0.9
+    assert s._alpha[1] == pytest.approx(a) and s._beta[1] == pytest.approx(b)
+    U = math.sqrt(a * b / ((a + b) ** 2 * (a + b + 1)))
+    assert s.topo_trust(1) == pytest.approx(a / (a + b) * math.exp(-5.0 * max(0, U - 0.3)))
+    s.update_trust(3, d=0, x=50)
+    assert s.topo_trust(3) < 0.05
+    assert s.model_score(1.0, 0.0) == 1.0 and s.model_score(0.5, 0.8) == pytest.approx(0.2 * 0.65 * math.exp(-0.3))
+    assert s.collab_score(1, 1.0) == pytest.approx(0.4 + 0.3 * s.topo_trust(1) + 0.2 * 0.5)
+    assert s.top_b([1, 2, 3], {1: 0.9, 3: 0.9}, 2) == [1, 3]
+    assert s.top_b([], {}, 3) == []
+    assert set(s.state_summary()) == {1, 2, 3}
+    assert verify_claim([1, 2, 5], {1, 2}) == (2.0, 1.0)
+    big = DMTTNodeState(0, DMTTConfig()); big.update_trust(7, 1, 0); assert big._alpha[7] == pytest.approx(1.9)
+
+
+def test_messaging_roundtrip():
+    from murmura_b200.distributed.messaging import MsgType, decode, decode_full, encode, pack_obj, pack_state, unpack_obj, unpack_state
+    import struct
+    frames = encode(MsgType.TOPO_CLAIM, 5, b"xyz", round_idx=9)
+    assert decode(frames) == (MsgType.TOPO_CLAIM, 5, b"xyz") and decode_full(frames)[2] == 9
+    legacy = [struct.pack("!Bi", 0, 3), b"p"]
+    assert decode_full(legacy) == (MsgType.MODEL_STATE, 3, -1, b"p")
+    st = {"w": torch.arange(4.0)}
+    assert torch.equal(unpack_state(pack_state(st))["w"], st["w"]) and unpack_obj(pack_obj({"a": 1})) == {"a": 1}
+    from murmura_b200.distributed.endpoints import Endpoints
+    from murmura_b200.config.schema import DistributedConfig
+    ep = Endpoints(DistributedConfig(transport="tcp", node_hosts={2: "10.0.0.2"}), 3, "r1")
+    assert ep.node_pull_connect(2) == "tcp://10.0.0.2:5552" and ep.node_pull_bind(1) == "tcp://0.0.0.0:5551"
+    assert Endpoints(DistributedConfig(), 3, "r1").monitor_pull_bind() == "ipc:///tmp/murmura/r1/monitor_pull"
+
+
+@pytest.mark.timeout(180)
+def test_zmq_distributed_backend(tmp_path):
+    """3 node processes + monitor over ipc:// — the reference's 'multi-node without a cluster' test bed."""
+    cfg = load_config(os.path.join(CFG, "distributed_fedavg.yaml"))
+    data = cfg.model_dump(); data["distributed"]["ipc_dir"] = str(tmp_path / "ipc")
+    import yaml
+    p = tmp_path / "dist.yaml"; p.write_text(yaml.safe_dump(data))
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    code = ("from murmura_b200.distributed import DistributedRunner; import sys;"
+            f"h = DistributedRunner('{p}').run(verbose=True); print('ROUNDS', h['round'], h['mean_accuracy'])")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=170)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ROUNDS [1, 2]" in res.stdout and "[Monitor] Round 2 (3/3 nodes)" in res.stdout
+
+
+@pytest.mark.timeout(240)
+def test_zmq_dmtt_backend(tmp_path):
+    cfg = load_config(os.path.join(CFG, "distributed_fedavg.yaml")).model_dump()
+    cfg["distributed"].update(ipc_dir=str(tmp_path / "ipc"), round_duration_s=6.0)
+    cfg["topology"]["num_nodes"] = 4
+    cfg["mobility"] = {"comm_range": 60.0, "seed": 1}
+    cfg["dmtt"] = {"budget_B": 2}
+    cfg["attack"] = {"enabled": True, "type": "topology_liar", "percentage": 0.25, "params": {"model_attack_type": "gaussian", "noise_std": 0.1}}
+    import yaml
+    p = tmp_path / "dmtt.yaml"; p.write_text(yaml.safe_dump(cfg))
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    code = f"from murmura_b200.distributed import DistributedRunner; h = DistributedRunner('{p}').run(verbose=True); print('ROUNDS', h['round'])"
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=230)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ROUNDS [1, 2]" in res.stdout
