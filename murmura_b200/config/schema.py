@@ -103,7 +103,7 @@ class B200Config(BaseModel):
         "reduce for full-mesh FedAvg; nccl = baseline send/recv + PyTorch aggregation")
     cuda_graphs: bool = Field(default=True, description="capture per-node train/eval steps in CUDA graphs")
     compute_dtype: Literal["fp32", "tf32", "bf16"] = Field(
-        default="tf32", description="matmul/conv math mode for local training (params stay fp32)")
+        default="fp32", description="matmul/conv math mode for local training (params stay fp32)")
     sketch_dtype: Literal["fp32", "fp8"] = Field(
         default="fp32", description="published Count-Sketch precision (fp8 = e4m3 + ue8m0 per 32)")
     krum_gram: Literal["auto", "tcgen05", "fp32"] = Field(
@@ -116,6 +116,9 @@ class B200Config(BaseModel):
     checkpoint_every: int = Field(default=0, description="save arena checkpoint every k rounds (0 = off)")
     checkpoint_dir: str = Field(default="checkpoints")
     profile: bool = Field(default=False, description="emit NVTX ranges + per-phase CUDA-event timings")
+    stream_inputs: bool = Field(
+        default=False, description="keep shards in pinned host memory and copy them H2D every round "
+        "(end-to-end mode); default keeps shards resident in HBM")
 
 
 class Config(BaseModel):

@@ -140,12 +140,18 @@ class B200Network:
 
         # ---- virtual nodes -------------------------------------------------------------------
         self.nodes: List[VirtualNode] = []
+        self._host_shards: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self.h2d_bytes_per_round = 0
         bs = config.training.batch_size
         for slot, gid in enumerate(self.local_gids):
             torch.manual_seed(config.experiment.seed * 1000003 + gid)       # per-node init stream, rank-layout independent
             model = model_factory().to(self.device)
             L.bind(model, self.live[slot], self.grad[slot], self.ints[slot] if L.Pi else None)
             X, y = dataset_adapter.client_tensors(gid)
+            if self.opt.stream_inputs:                      # end-to-end mode: shards live in pinned host memory
+                xh, yh = X.float().contiguous().pin_memory(), y.long().contiguous().pin_memory()
+                self._host_shards.append((xh, yh))
+                self.h2d_bytes_per_round += xh.numel() * 4 + yh.numel() * 8
             X = X.to(self.device, non_blocking=True).float().contiguous()
             y = y.to(self.device, non_blocking=True).long().contiguous()
             n = int(y.shape[0])
@@ -342,13 +348,18 @@ class B200Network:
 
     def _local_training(self, epochs: int, lr: float) -> None:
         from murmura_b200.models.mlp import EvidentialLoss
+        self._fused_evidential = self.evidential and isinstance(self.criterion, EvidentialLoss)
         if isinstance(self.criterion, EvidentialLoss):
             self.lam_t.fill_(self.criterion.anneal(self.round_idx))
         self._fork()
         for i, vn in enumerate(self.nodes):
+            stream = self.streams[i % len(self.streams)]
+            if self._host_shards:                             # per-round H2D of this node's inputs (pinned → HBM)
+                with torch.cuda.stream(stream):
+                    vn.X.copy_(self._host_shards[i][0], non_blocking=True)
+                    vn.y.copy_(self._host_shards[i][1], non_blocking=True)
             if vn.byzantine or vn.nb == 0:
                 continue
-            stream = self.streams[i % len(self.streams)]
             with torch.cuda.stream(stream):
                 take = vn.nb * vn.eb
                 keys = torch.rand(epochs, vn.n, device=self.device)
@@ -360,7 +371,7 @@ class B200Network:
                         vn.train_graph.replay()
                     else:
                         self._train_step(vn, lr)
-                self.kernel_launches += epochs * vn.nb
+                self.kernel_launches += epochs * vn.nb * (2 if self._fused_evidential else 1)
         self._join()
 
     # =========================================================================================
@@ -702,7 +713,7 @@ class B200Network:
                     vn.eval_graph.replay()
                 else:
                     self._eval_node(vn)
-                self.kernel_launches += 1
+                self.kernel_launches += (vn.n + max(1, self.opt.eval_batch) - 1) // max(1, self.opt.eval_batch)
         self._join()
         S = self.placement.slots_per_rank
         local = torch.zeros(S, _STAT_COLS, device=self.device)

@@ -1,0 +1,257 @@
+"""B200 engine on one GPU: fused aggregation vs the CPU oracle classes, end-to-end training, checkpoints."""
+import copy
+import math
+import re
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from murmura_b200 import Network
+from murmura_b200.config import Config
+from murmura_b200.utils.factories import (build_aggregator_factory, build_criterion, build_dataset_adapter,
+                                          build_model_factory)
+
+
+def _cfg(algo="fedavg", params=None, n=6, topo=None, attack=None, model=None, data=None, b200=None, rounds=3, **extra):
+    base = {"experiment": {"name": "t", "rounds": rounds, "seed": 3},
+            "topology": topo or {"type": "k-regular", "num_nodes": n, "k": 2},
+            "aggregation": {"algorithm": algo, "params": params or {}},
+            "training": {"batch_size": 32, "lr": 0.05, "local_epochs": 1},
+            "data": data or {"adapter": "synthetic.mnist", "params": {"samples_per_node": 24, "partition_method": "iid"}},
+            "model": model or {"factory": "models.mlp", "params": {"hidden_dims": [32]}},
+            "backend": "b200", "b200": b200 or {}}
+    if attack:
+        base["attack"] = attack
+    base.update(extra)
+    return Config(**base)
+
+
+def _build(cfg):
+    adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
+    crit, evid = build_criterion(cfg)
+    net = Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf, torch.device("cuda")),
+                              device=torch.device("cuda"), criterion=crit, evidential=evid)
+    return net, adapter, mf
+
+
+HAR = {"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6, "hidden_dims": [32, 16]}}
+HAR_DATA = {"adapter": "wearables.uci_har", "params": {"data_path": "synthetic", "samples_per_node": 24, "partition_method": "iid"}}
+
+
+def _oracle_round(net, cfg, adapter, mf, parity=0):
+    """Run the fused aggregation once and the CPU aggregator classes on the same inputs; return both results."""
+    L = net.layout
+    for vn in net.nodes:                                             # decorrelate node states + non-trivial int buffers
+        net.live[vn.slot, :L.Pf] += 0.05 * (vn.gid + 1) * torch.randn(L.Pf, device=net.device)
+        if L.Pi:
+            net.ints[vn.slot] = torch.arange(L.Pi, device=net.device) + 3 * vn.gid
+    own = {vn.gid: {k: v.detach().cpu().clone() for k, v in L.row_views(net.live[vn.slot], net.ints[vn.slot]).items()} for vn in net.nodes}
+    net._aggregate(parity=parity)
+    torch.cuda.synchronize()
+    pub = {}
+    for vn in net.nodes:
+        row = net.arena.pub[parity, vn.slot]
+        st = {k: v.detach().cpu().clone() for k, v in L.row_views(row, None).items()}
+        for e in L.int_entries():
+            st[e.name] = row[L.Pf_pad + e.offset: L.Pf_pad + e.offset + e.numel].round().long().view(e.shape).cpu()
+        pub[vn.gid] = st
+    got = {vn.gid: {k: v.detach().cpu().clone() for k, v in L.row_views(net.live[vn.slot], net.ints[vn.slot]).items()} for vn in net.nodes}
+    agg_factory = build_aggregator_factory(cfg, mf, torch.device("cpu"))
+    crit, evid = build_criterion(cfg)
+    want = {}
+    for vn in net.nodes:
+        agg = agg_factory(vn.gid)
+        template = mf()
+        loader = [(vn.X.cpu(), vn.y.cpu())]
+        nbrs = {j: pub[j] for j in net.topology.neighbors[vn.gid]}
+        out = agg.aggregate(node_id=vn.gid, own_state=own[vn.gid], neighbor_states=nbrs, round_num=net.round_idx,
+                            train_loader=loader, model_template=template, device=torch.device("cpu"))
+        template.load_state_dict(out)                                # int buffers are cast back like load_state_dict does
+        want[vn.gid] = {k: v.clone() for k, v in template.state_dict().items()}
+    return got, want, own, pub
+
+
+def _assert_states_close(got, want, atol=2e-5):
+    for gid in want:
+        for k in want[gid]:
+            a, b = got[gid][k], want[gid][k]
+            if b.is_floating_point():
+                assert torch.allclose(a.float(), b.float(), rtol=1e-4, atol=atol), (gid, k, (a.float() - b.float()).abs().max())
+            else:
+                assert torch.equal(a.long(), b.long()), (gid, k, a, b)
+
+
+@pytest.mark.parametrize("algo,params,attack", [
+    ("fedavg", {}, None),
+    ("fedavg", {}, {"enabled": True, "type": "directed_deviation", "percentage": 0.34, "params": {"lambda_param": -5.0}}),
+    ("balance", {"gamma": 0.3, "kappa": 1.0, "alpha": 0.5}, {"enabled": True, "type": "directed_deviation", "percentage": 0.34}),
+    ("krum", {"num_compromised": 1}, {"enabled": True, "type": "gaussian", "percentage": 0.34, "params": {"noise_std": 1.0}}),
+    ("sketchguard", {"sketch_size": 256, "gamma": 0.3, "alpha": 0.5}, {"enabled": True, "type": "directed_deviation", "percentage": 0.34}),
+    ("ubar", {"rho": 0.6, "alpha": 0.5}, {"enabled": True, "type": "directed_deviation", "percentage": 0.34}),
+])
+def test_fused_aggregation_matches_cpu_oracle_bn_model(algo, params, attack):
+    cfg = _cfg(algo, params, n=6, topo={"type": "k-regular", "num_nodes": 6, "k": 4}, attack=attack, model=HAR, data=HAR_DATA,
+               b200={"krum_gram": "fp32"})
+    net, adapter, mf = _build(cfg)
+    try:
+        got, want, own, pub = _oracle_round(net, cfg, adapter, mf)
+        _assert_states_close(got, want)
+        if attack and attack["type"] == "directed_deviation":
+            byz = sorted(net.compromised)[0]
+            k = next(iter(own[byz]))
+            assert torch.allclose(pub[byz][k], -5.0 * own[byz][k], atol=1e-5)
+    finally:
+        net.close()
+
+
+def test_fused_evidential_trust_matches_cpu_oracle():
+    cfg = _cfg("evidential_trust", {"trust_threshold": 0.05, "self_weight": 0.6, "accuracy_weight": 0.7}, n=5,
+               topo={"type": "fully", "num_nodes": 5}, model=HAR, data=HAR_DATA)
+    net, adapter, mf = _build(cfg)
+    try:
+        got, want, _, _ = _oracle_round(net, cfg, adapter, mf)
+        _assert_states_close(got, want, atol=5e-5)
+    finally:
+        net.close()
+
+
+def test_krum_tcgen05_gram_path_agrees_with_fp32_path():
+    res = {}
+    for mode in ("fp32", "tcgen05"):
+        cfg = _cfg("krum", {"num_compromised": 1}, n=10, topo={"type": "k-regular", "num_nodes": 10, "k": 4},
+                   attack={"enabled": True, "type": "gaussian", "percentage": 0.3, "params": {"noise_std": 5.0}},
+                   model={"factory": "models.mlp", "params": {"hidden_dims": [64]}}, b200={"krum_gram": mode})
+        torch.manual_seed(0)
+        net, adapter, mf = _build(cfg)
+        try:
+            got, want, _, _ = _oracle_round(net, cfg, adapter, mf)
+            _assert_states_close(got, want)
+            res[mode] = got
+        finally:
+            net.close()
+    for gid in res["fp32"]:
+        for k in res["fp32"][gid]:
+            assert torch.equal(res["fp32"][gid][k], res["tcgen05"][gid][k])
+
+
+def test_end_to_end_training_and_contract(capsys):
+    cfg = _cfg("fedavg", n=8, topo={"type": "ring", "num_nodes": 8}, rounds=4,
+               data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "dirichlet", "alpha": 0.5}})
+    net, _, _ = _build(cfg)
+    try:
+        hist = net.train(rounds=4, local_epochs=1, lr=0.05, verbose=True)
+        out = capsys.readouterr().out
+        assert hist["round"] == [1, 2, 3, 4] and hist["mean_accuracy"][-1] > hist["mean_accuracy"][0]
+        assert hist["mean_accuracy"][-1] > 0.5
+        assert re.search(r"Round 4: Mean Accuracy = \d\.\d{4} ± \d\.\d{4}", out) and "=== Round 1/4 ===" in out
+        assert set(net.get_node_statistics()) == set(range(8))
+    finally:
+        net.close()
+
+
+def test_graphs_match_eager_and_simulation_statistically():
+    accs = {}
+    for graphs in (True, False):
+        cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, b200={"cuda_graphs": graphs},
+                   data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}})
+        net, _, _ = _build(cfg)
+        try:
+            accs[graphs] = net.train(rounds=3, lr=0.05)["mean_accuracy"][-1]
+        finally:
+            net.close()
+    sim_cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4},
+                   data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}}, backend="simulation")
+    adapter = build_dataset_adapter(sim_cfg); mf = build_model_factory(sim_cfg)
+    sim = Network.from_config(sim_cfg, mf, adapter, build_aggregator_factory(sim_cfg, mf), device=torch.device("cpu"))
+    accs["sim"] = sim.train(rounds=3, lr=0.05)["mean_accuracy"][-1]
+    assert abs(accs[True] - accs[False]) < 0.1 and abs(accs[True] - accs["sim"]) < 0.15, accs
+
+
+def test_evidential_training_with_device_annealing():
+    cfg = _cfg("fedavg", n=4, topo={"type": "ring", "num_nodes": 4}, model=HAR,
+               data={"adapter": "wearables.uci_har", "params": {"data_path": "synthetic", "samples_per_node": 96, "partition_method": "iid"}}, rounds=4)
+    net, _, _ = _build(cfg)
+    try:
+        hist = net.train(rounds=4, lr=0.05)
+        assert len(hist["mean_vacuity"]) == 4 and hist["mean_accuracy"][-1] > 0.3
+        assert 0 < hist["mean_vacuity"][-1] <= 1.0 and hist["mean_strength"][-1] >= 6.0
+    finally:
+        net.close()
+
+
+def test_byzantine_nodes_frozen_and_checkpoint_roundtrip(tmp_path):
+    cfg = _cfg("balance", {"gamma": 0.5}, n=6, attack={"enabled": True, "type": "gaussian", "percentage": 0.34, "params": {"noise_std": 10.0}})
+    net, _, _ = _build(cfg)
+    try:
+        hist = net.train(rounds=2, lr=0.05)
+        assert len(hist["honest_accuracy"]) == 2 and len(hist["compromised_accuracy"]) == 2
+        net.save_checkpoint(str(tmp_path / "ck"))
+        snap = net.live.clone(); r = net.round_idx
+        net.train(rounds=1, lr=0.05)
+        assert not torch.equal(snap, net.live)
+        net.load_checkpoint(str(tmp_path / "ck"))
+        assert torch.equal(snap[: net.V], net.live[: net.V]) and net.round_idx == r
+    finally:
+        net.close()
+
+
+def test_fault_injection_drops_edge():
+    cfg = _cfg("fedavg", n=3, topo={"type": "fully", "num_nodes": 3}, b200={"fault_drop_edges": {0: [[1, 0]]}})
+    net, adapter, mf = _build(cfg)
+    try:
+        L = net.layout
+        net.live[:, :L.Pf] = torch.tensor([[1.0], [2.0], [6.0]], device=net.device)
+        net._aggregate(parity=0); torch.cuda.synchronize()
+        assert net.live[0, 0].item() == pytest.approx(3.5)           # node 0 lost the edge from node 1 → mean(1, 6)
+        assert net.live[1, 0].item() == pytest.approx(3.0) and net.live[2, 0].item() == pytest.approx(3.0)
+    finally:
+        net.close()
+
+
+def test_mobility_and_dmtt_on_device():
+    cfg = _cfg("fedavg", n=8, topo={"type": "ring", "num_nodes": 8}, rounds=3,
+               attack={"enabled": True, "type": "topology_liar", "percentage": 0.25, "params": {"model_attack_type": "gaussian", "noise_std": 1.0}},
+               mobility={"comm_range": 45.0, "seed": 1}, dmtt={"budget_B": 2})
+    net, _, _ = _build(cfg)
+    try:
+        hist = net.train(rounds=3, lr=0.05)
+        assert hist["round"] == [1, 2, 3]
+        collab = net.collab.cpu().numpy()
+        assert collab.shape == (8, 8) and (collab.sum(1) <= 2).all() and collab.diagonal().sum() == 0
+        honest = [i for i in range(8) if i not in net.compromised]
+        liars = sorted(net.compromised)
+        # trust in liars' topology claims decays relative to honest peers
+        a, b = net.t_alpha.cpu().numpy(), net.t_beta.cpu().numpy()
+        R = a / (a + b)
+        seen_liar = [R[i, j] for i in honest for j in liars if b[i, j] != 1.0 or a[i, j] != 1.0]
+        seen_honest = [R[i, j] for i in honest for j in honest if i != j and (b[i, j] != 1.0 or a[i, j] != 1.0)]
+        if seen_liar and seen_honest:
+            assert np.mean(seen_liar) <= np.mean(seen_honest) + 1e-6
+    finally:
+        net.close()
+
+
+def test_custom_aggregator_and_attack_fall_back_to_generic_path():
+    from murmura_b200.aggregation import Aggregator
+
+    class TakeMax(Aggregator):
+        def aggregate(self, node_id, own_state, neighbor_states, round_num, **kw):
+            out = {}
+            for k, v in own_state.items():
+                out[k] = torch.stack([v] + [s[k] for s in neighbor_states.values()]).max(0).values if v.is_floating_point() else v
+            return out
+
+    cfg = _cfg("fedavg", n=3, topo={"type": "fully", "num_nodes": 3})
+    adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
+    net = Network.from_config(cfg, mf, adapter, lambda nid: TakeMax(), device=torch.device("cuda"))
+    try:
+        assert net.family == "generic"
+        L = net.layout
+        net.live[:, :L.Pf] = torch.tensor([[1.0], [2.0], [6.0]], device=net.device)
+        net._aggregate(parity=0); torch.cuda.synchronize()
+        assert (net.live[:, :L.Pf] == 6.0).all()
+    finally:
+        net.close()
