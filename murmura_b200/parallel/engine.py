@@ -180,6 +180,15 @@ class B200Network:
         # ---- streams / buffers ---------------------------------------------------------------
         self.main = torch.cuda.current_stream(self.device)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, self.opt.streams))]
+        # One capture stream per worker stream.  cuBLAS keeps one workspace per (handle, stream); graphs captured on
+        # the same stream bake in the same workspace pointer, so graphs that may REPLAY concurrently must have been
+        # captured on different streams (graphs of one worker stream replay back-to-back and may share).  The
+        # workspaces are created here, outside any capture, so they are not owned by a graph's private pool.
+        self.capture_streams = [torch.cuda.Stream(self.device) for _ in self.streams]
+        for cs in self.capture_streams:
+            with torch.cuda.stream(cs):
+                torch.mm(torch.ones(64, 64, device=self.device), torch.ones(64, 64, device=self.device))
+        torch.cuda.synchronize(self.device)
         self.eval_stats = torch.zeros(max(self.V, 1), _STAT_COLS, device=self.device)
         self.metrics_host = torch.zeros(self.placement.slots_per_rank * self.world, _STAT_COLS).pin_memory()
         self.lam_t = torch.zeros((), device=self.device)
@@ -321,7 +330,7 @@ class B200Network:
         rng = torch.cuda.get_rng_state(self.device)
         vn.model.train()
         vn.perm_buf.copy_(torch.arange(vn.perm_buf.numel(), device=self.device) % vn.n)
-        side = torch.cuda.Stream(self.device)
+        side = self.capture_streams[vn.slot % len(self.capture_streams)]
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
@@ -330,7 +339,7 @@ class B200Network:
         torch.cuda.current_stream().wait_stream(side)
         vn.step.zero_()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             self._train_step(vn, lr)
         vn.train_graph = graph
         self.live[vn.slot].copy_(snap); self.ints[vn.slot].copy_(snap_i)
@@ -739,13 +748,13 @@ class B200Network:
         return per_node
 
     def _capture_eval(self, vn: VirtualNode) -> None:
-        side = torch.cuda.Stream(self.device)
+        side = self.capture_streams[vn.slot % len(self.capture_streams)]
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._eval_node(vn)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             self._eval_node(vn)
         vn.eval_graph = g
 

@@ -45,7 +45,8 @@ def _oracle_round(net, cfg, adapter, mf, parity=0):
     """Run the fused aggregation once and the CPU aggregator classes on the same inputs; return both results."""
     L = net.layout
     for vn in net.nodes:                                             # decorrelate node states + non-trivial int buffers
-        net.live[vn.slot, :L.Pf] += 0.05 * (vn.gid + 1) * torch.randn(L.Pf, device=net.device)
+        for e in L.float_entries():                                  # (only real entries: padding must stay zero)
+            net.live[vn.slot, e.offset:e.offset + e.numel] += 0.05 * (vn.gid + 1) * torch.randn(e.numel, device=net.device)
         if L.Pi:
             net.ints[vn.slot] = torch.arange(L.Pi, device=net.device) + 3 * vn.gid
     own = {vn.gid: {k: v.detach().cpu().clone() for k, v in L.row_views(net.live[vn.slot], net.ints[vn.slot]).items()} for vn in net.nodes}
@@ -72,6 +73,12 @@ def _oracle_round(net, cfg, adapter, mf, parity=0):
         template.load_state_dict(out)                                # int buffers are cast back like load_state_dict does
         want[vn.gid] = {k: v.clone() for k, v in template.state_dict().items()}
     return got, want, own, pub
+
+
+def _fill(net, values):
+    for e in net.layout.float_entries():
+        for slot, val in enumerate(values):
+            net.live[slot, e.offset:e.offset + e.numel] = val
 
 
 def _assert_states_close(got, want, atol=2e-5):
@@ -154,32 +161,45 @@ def test_end_to_end_training_and_contract(capsys):
 
 def test_graphs_match_eager_and_simulation_statistically():
     accs = {}
+    data = {"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}}
     for graphs in (True, False):
-        cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, b200={"cuda_graphs": graphs},
-                   data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}})
+        cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, b200={"cuda_graphs": graphs, "streams": 4}, data=data)
         net, _, _ = _build(cfg)
         try:
-            accs[graphs] = net.train(rounds=3, lr=0.05)["mean_accuracy"][-1]
+            accs[graphs] = net.train(rounds=8, lr=0.05)["mean_accuracy"]
         finally:
             net.close()
-    sim_cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4},
-                   data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}}, backend="simulation")
+    assert accs[True] == accs[False]            # same RNG streams, same kernels: CUDA graphs on 4 streams are bit-identical to eager
+    sim_cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, data=data, backend="simulation")
     adapter = build_dataset_adapter(sim_cfg); mf = build_model_factory(sim_cfg)
+    torch.manual_seed(3)
     sim = Network.from_config(sim_cfg, mf, adapter, build_aggregator_factory(sim_cfg, mf), device=torch.device("cpu"))
-    accs["sim"] = sim.train(rounds=3, lr=0.05)["mean_accuracy"][-1]
-    assert abs(accs[True] - accs[False]) < 0.1 and abs(accs[True] - accs["sim"]) < 0.15, accs
+    accs["sim"] = sim.train(rounds=8, lr=0.05)["mean_accuracy"]
+    assert abs(accs[True][-1] - accs["sim"][-1]) < 0.12 and accs[True][-1] > 0.6, accs
 
 
 def test_evidential_training_with_device_annealing():
-    cfg = _cfg("fedavg", n=4, topo={"type": "ring", "num_nodes": 4}, model=HAR,
-               data={"adapter": "wearables.uci_har", "params": {"data_path": "synthetic", "samples_per_node": 96, "partition_method": "iid"}}, rounds=4)
+    """BN + dropout + fused evidential loss (device-side annealing) inside CUDA graphs tracks the CPU simulation."""
+    data = {"adapter": "wearables.uci_har", "params": {"data_path": "synthetic", "samples_per_node": 256, "partition_method": "iid"}}
+    kw = dict(n=4, topo={"type": "ring", "num_nodes": 4}, model=HAR, data=data, rounds=6)
+    cfg = _cfg("fedavg", **kw)
+    cfg.training.local_epochs = 2
     net, _, _ = _build(cfg)
     try:
-        hist = net.train(rounds=4, lr=0.05)
-        assert len(hist["mean_vacuity"]) == 4 and hist["mean_accuracy"][-1] > 0.3
-        assert 0 < hist["mean_vacuity"][-1] <= 1.0 and hist["mean_strength"][-1] >= 6.0
+        hist = net.train(rounds=6, local_epochs=2, lr=0.05)
     finally:
         net.close()
+    assert len(hist["mean_vacuity"]) == 6 and 0 < hist["mean_vacuity"][-1] <= 1.0 and hist["mean_strength"][-1] >= 6.0
+    sim_cfg = _cfg("fedavg", backend="simulation", **kw)
+    adapter = build_dataset_adapter(sim_cfg); mf = build_model_factory(sim_cfg)
+    crit, evid = build_criterion(sim_cfg)
+    torch.manual_seed(3)
+    sim = Network.from_config(sim_cfg, mf, adapter, build_aggregator_factory(sim_cfg, mf), device=torch.device("cpu"),
+                              criterion=crit, evidential=evid)
+    ref = sim.train(rounds=6, local_epochs=2, lr=0.05)
+    assert hist["mean_accuracy"][-1] > 1.0 / 6 + 0.1, hist["mean_accuracy"]
+    assert abs(hist["mean_accuracy"][-1] - ref["mean_accuracy"][-1]) < 0.15, (hist["mean_accuracy"], ref["mean_accuracy"])
+    assert abs(hist["mean_vacuity"][-1] - ref["mean_vacuity"][-1]) < 0.05
 
 
 def test_byzantine_nodes_frozen_and_checkpoint_roundtrip(tmp_path):
@@ -203,7 +223,7 @@ def test_fault_injection_drops_edge():
     net, adapter, mf = _build(cfg)
     try:
         L = net.layout
-        net.live[:, :L.Pf] = torch.tensor([[1.0], [2.0], [6.0]], device=net.device)
+        _fill(net, [1.0, 2.0, 6.0])
         net._aggregate(parity=0); torch.cuda.synchronize()
         assert net.live[0, 0].item() == pytest.approx(3.5)           # node 0 lost the edge from node 1 → mean(1, 6)
         assert net.live[1, 0].item() == pytest.approx(3.0) and net.live[2, 0].item() == pytest.approx(3.0)
@@ -250,8 +270,9 @@ def test_custom_aggregator_and_attack_fall_back_to_generic_path():
     try:
         assert net.family == "generic"
         L = net.layout
-        net.live[:, :L.Pf] = torch.tensor([[1.0], [2.0], [6.0]], device=net.device)
+        _fill(net, [1.0, 2.0, 6.0])
         net._aggregate(parity=0); torch.cuda.synchronize()
-        assert (net.live[:, :L.Pf] == 6.0).all()
+        for e in L.float_entries():
+            assert (net.live[:, e.offset:e.offset + e.numel] == 6.0).all()
     finally:
         net.close()

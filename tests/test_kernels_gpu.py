@@ -279,10 +279,11 @@ def test_filters_match_cpu_aggregators(ext):
 def test_sketchguard_filter_kernel(ext):
     V, K = 3, 200
     g = torch.Generator().manual_seed(13)
-    own = torch.randn(V, K, generator=g)
+    base = torch.randn(K, generator=g)
+    own = base + 0.05 * torch.randn(V, K, generator=g)               # all honest nodes sit near a common model
     pubsk = torch.zeros(2, V, K)
-    pubsk[1] = own + 0.05 * torch.randn(V, K, generator=g)
-    pubsk[1, 2] = own[2] * -5.0
+    pubsk[1] = own + 0.01 * torch.randn(V, K, generator=g)
+    pubsk[1, 2] = own[2] * -5.0                                       # node 2 publishes a directed-deviation sketch
     own_d = own.to(DEV); pub_d = pubsk.to(DEV)
     et_n = [[1, 2], [0, 2], [0, 1]]
     rows, slots = [0], []
