@@ -23,8 +23,8 @@ HAR_DATA = {"adapter": "wearables.uci_har", "params": {"data_path": "synthetic",
 ATTACK = {"enabled": True, "type": "directed_deviation", "percentage": 0.3, "params": {"lambda_param": -5.0}}
 
 
-def det_state(layout, gid, device):
-    g = torch.Generator().manual_seed(1234 + gid)
+def det_state(layout, gid, rnd=0):
+    g = torch.Generator().manual_seed(1234 + gid + 1000 * rnd)
     row = torch.zeros(layout.stride)
     for e in layout.float_entries():
         base = torch.linspace(-1, 1, e.numel) * 0.1
@@ -54,7 +54,7 @@ def check(algo, params, n, topo, b200=None, attack=ATTACK, rounds=2):
     worst = 0.0
     for r in range(rounds):
         net.round_idx = r
-        rows = {g: det_state(L, g + 100 * r, net.device) for g in range(n)}
+        rows = {g: det_state(L, g, r) for g in range(n)}
         for vn in net.nodes:
             net.live[vn.slot].copy_(rows[vn.gid][0]); net.ints[vn.slot].copy_(rows[vn.gid][1][: net.ints.shape[1]])
         net._aggregate(parity=r & 1)
