@@ -28,6 +28,39 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ live,
     }
 }
 
+// ---- multi-tensor SGD: θ_t -= lr·g_t for up to 64 (param, grad) pairs in ONE launch ----------------------
+// Gradients stay wherever autograd produced them (no accumulate-into-arena pass); pointers travel in the kernel
+// parameter block, so the launch is CUDA-graph capturable with zero device-side tables.
+constexpr int kMtTensors = 64;
+constexpr int kMtBlocks = 320;
+constexpr int kMtChunk = 65536;                   // floats per block
+struct MultiSgdArgs {
+    float* p[kMtTensors];
+    const float* g[kMtTensors];
+    int n[kMtTensors];
+    unsigned char block_tensor[kMtBlocks];
+    int block_chunk[kMtBlocks];
+};
+__global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ MultiSgdArgs a, float lr) {
+    const int t = a.block_tensor[blockIdx.x];
+    const int base = a.block_chunk[blockIdx.x] * kMtChunk;
+    const int n = min(a.n[t] - base, kMtChunk);
+    float* __restrict__ p = a.p[t] + base;
+    const float* __restrict__ g = a.g[t] + base;
+    if ((((uintptr_t)p | (uintptr_t)g) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 w = reinterpret_cast<float4*>(p)[i];
+            const float4 d = reinterpret_cast<const float4*>(g)[i];
+            w.x = fmaf(-lr, d.x, w.x); w.y = fmaf(-lr, d.y, w.y); w.z = fmaf(-lr, d.z, w.z); w.w = fmaf(-lr, d.w, w.w);
+            reinterpret_cast<float4*>(p)[i] = w;
+        }
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) p[i] = fmaf(-lr, g[i], p[i]);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = fmaf(-lr, g[i], p[i]);
+    }
+}
+
 // ---- softmax cross-entropy evaluation: one warp per row, device-side accumulators ----------------
 // stats[0] += Σ CE, stats[1] += #correct, stats[2] += #rows  (rows >= n_valid are padding)
 __global__ void ce_eval_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
@@ -152,6 +185,36 @@ void sgd_step(Tensor live, int64_t stride, Tensor grad, int64_t gstride, int64_t
     mb::sgd_step_kernel<<<grid, 256, 0, cur_stream()>>>(live.data_ptr<float>() + (size_t)slot0 * stride, (size_t)stride,
                                                          grad.data_ptr<float>() + (size_t)slot0 * gstride, (size_t)gstride, n4, (float)lr);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// params[i] / grads[i]: dense tensors with identical physical layout (checked by the caller)
+void sgd_multi(std::vector<Tensor> params, std::vector<Tensor> grads, double lr) {
+    TORCH_CHECK(params.size() == grads.size());
+    if (params.empty()) return;
+    c10::cuda::CUDAGuard guard(params[0].device());
+    struct Piece { float* p; const float* g; int64_t n; };
+    std::vector<Piece> pieces;
+    const int64_t max_piece = (int64_t)mb::kMtBlocks * mb::kMtChunk;          // one launch worth of one tensor
+    for (size_t i = 0; i < params.size(); ++i) {
+        const int64_t n = params[i].numel();
+        TORCH_CHECK(n == grads[i].numel(), "sgd_multi: size mismatch");
+        float* p = params[i].data_ptr<float>(); const float* g = grads[i].data_ptr<float>();
+        for (int64_t off = 0; off < n; off += max_piece) pieces.push_back({p + off, g + off, std::min(max_piece, n - off)});
+    }
+    size_t i = 0;
+    while (i < pieces.size()) {
+        mb::MultiSgdArgs a;
+        int nt = 0, nb = 0;
+        while (i < pieces.size() && nt < mb::kMtTensors) {
+            const int chunks = (int)((pieces[i].n + mb::kMtChunk - 1) / mb::kMtChunk);
+            if (nb + chunks > mb::kMtBlocks) break;
+            a.p[nt] = pieces[i].p; a.g[nt] = pieces[i].g; a.n[nt] = (int)pieces[i].n;
+            for (int c = 0; c < chunks; ++c) { a.block_tensor[nb] = (unsigned char)nt; a.block_chunk[nb] = c; ++nb; }
+            ++nt; ++i;
+        }
+        mb::sgd_multi_kernel<<<nb, 256, 0, cur_stream()>>>(a, (float)lr);
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
+    }
 }
 
 void ce_eval(Tensor logits, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats) {

@@ -32,6 +32,14 @@ class Entry:
     offset: int          # element offset inside the row (float region) or inside the int table
     kind: str            # "param" | "fbuf" | "int"
     ref_offset: int = -1  # offset in the reference's flatten order (float tensors, state_dict order)
+    channels_last: bool = False   # 4-D weights stored physically as (O, H, W, I) for the NHWC tensor-core conv path
+
+    def view(self, row: torch.Tensor) -> torch.Tensor:
+        flat = row[self.offset:self.offset + self.numel]
+        if self.channels_last:
+            o, i, h, w = self.shape
+            return flat.view(o, h, w, i).permute(0, 3, 1, 2)      # logical (O,I,H,W) with channels_last strides
+        return flat.view(self.shape)
 
 
 @dataclass
@@ -47,7 +55,7 @@ class StateLayout:
     P_float_real: int = 0  # number of float state elements (reference's "model_dim")
 
     @classmethod
-    def from_model(cls, model: nn.Module) -> "StateLayout":
+    def from_model(cls, model: nn.Module, channels_last: bool = False) -> "StateLayout":
         lay = cls()
         param_names = {n for n, _ in model.named_parameters()}
         state = model.state_dict()
@@ -61,7 +69,8 @@ class StateLayout:
         off = 0
         for name, t in state.items():
             if name in param_names:
-                lay.entries.append(Entry(name, tuple(t.shape), t.numel(), off, "param", ref_offsets[name]))
+                lay.entries.append(Entry(name, tuple(t.shape), t.numel(), off, "param", ref_offsets[name],
+                                         channels_last=channels_last and t.dim() == 4))
                 off += t.numel()
         lay.Pp = off
         lay.Pp4 = _ceil(off, 4)
@@ -96,14 +105,17 @@ class StateLayout:
                 if ints is not None:
                     out[e.name] = ints[e.offset:e.offset + e.numel].view(e.shape)
             else:
-                out[e.name] = row[e.offset:e.offset + e.numel].view(e.shape)
+                out[e.name] = e.view(row)
         return out
 
     def ref_permutation(self) -> np.ndarray:
         """``perm[arena_pos] = reference flatten index`` for real float elements, -1 for padding."""
         perm = np.full(self.Pf, -1, dtype=np.int64)
         for e in self.float_entries():
-            perm[e.offset:e.offset + e.numel] = np.arange(e.ref_offset, e.ref_offset + e.numel)
+            logical = np.arange(e.ref_offset, e.ref_offset + e.numel)
+            if e.channels_last:                       # physical order is (O,H,W,I); the reference flattens (O,I,H,W)
+                logical = logical.reshape(e.shape).transpose(0, 2, 3, 1).ravel()
+            perm[e.offset:e.offset + e.numel] = logical
         return perm
 
     def bind(self, model: nn.Module, row: torch.Tensor, grad_row: Optional[torch.Tensor], ints: Optional[torch.Tensor]) -> None:
@@ -114,11 +126,11 @@ class StateLayout:
             for e in self.entries:
                 if e.kind == "param":
                     p = params[e.name]
-                    view = row[e.offset:e.offset + e.numel].view(e.shape)
+                    view = e.view(row)
                     view.copy_(p.detach())
                     p.data = view
                     if grad_row is not None:
-                        p.grad = grad_row[e.offset:e.offset + e.numel].view(e.shape)
+                        p.grad = e.view(grad_row)
                 else:
                     mod_name, _, leaf = e.name.rpartition(".")
                     mod = modules[mod_name]

@@ -75,6 +75,8 @@ class VirtualNode:
     eb: int                 # effective batch size  min(bs, max(2, n))
     nb: int                 # batches per epoch (drop_last when n > eb)
     byzantine: bool = False
+    nhwc: bool = False
+    params: List[nn.Parameter] = field(default_factory=list)
     perm_buf: Optional[torch.Tensor] = None
     step: Optional[torch.Tensor] = None
     arange: Optional[torch.Tensor] = None
@@ -127,13 +129,12 @@ class B200Network:
         # ---- arena ---------------------------------------------------------------------------
         self.placement = Placement(self.N, self.world)
         probe = model_factory()
-        self.layout = StateLayout.from_model(probe)
+        self.layout = StateLayout.from_model(probe, channels_last=bool(self.opt.channels_last))
         sketch_k = int(getattr(self.aggregator, "sketch_size", 0)) if self.family == "sketchguard" else 0
         self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k)
         S, L = self.placement.slots_per_rank, self.layout
         self.S = S
         self.live = self.arena.live
-        self.grad = torch.zeros(S, L.Pp4, device=self.device)
         self.ints = torch.zeros(S, max(L.Pi, 1), dtype=torch.int64, device=self.device)
         self.local_gids = self.placement.local_nodes(self.rank)
         self.V = len(self.local_gids)
@@ -146,8 +147,11 @@ class B200Network:
         for slot, gid in enumerate(self.local_gids):
             torch.manual_seed(config.experiment.seed * 1000003 + gid)       # per-node init stream, rank-layout independent
             model = model_factory().to(self.device)
-            L.bind(model, self.live[slot], self.grad[slot], self.ints[slot] if L.Pi else None)
+            L.bind(model, self.live[slot], None, self.ints[slot] if L.Pi else None)
             X, y = dataset_adapter.client_tensors(gid)
+            nhwc = bool(self.opt.channels_last) and X.dim() == 4
+            if nhwc:
+                X = X.permute(0, 2, 3, 1)                   # keep image shards physically NHWC
             if self.opt.stream_inputs:                      # end-to-end mode: shards live in pinned host memory
                 xh, yh = X.float().contiguous().pin_memory(), y.long().contiguous().pin_memory()
                 self._host_shards.append((xh, yh))
@@ -159,7 +163,8 @@ class B200Network:
             nb = (n // eb) if n > eb else (1 if n >= 2 else 0)
             eb = min(eb, n) if n >= 2 else eb
             self.nodes.append(VirtualNode(gid=gid, slot=slot, model=model, X=X, y=y, n=n, eb=eb, nb=nb,
-                                          byzantine=gid in self.compromised))
+                                          byzantine=gid in self.compromised, nhwc=nhwc,
+                                          params=[p for p in model.parameters() if p.requires_grad]))
         del probe
         torch.manual_seed(config.experiment.seed + 7919 * self.rank)
 
@@ -291,15 +296,27 @@ class B200Network:
             return self.criterion(out.float(), yb, epoch=self.round_idx)
         return F.cross_entropy(out.float(), yb)
 
+    @staticmethod
+    def _inputs(vn: VirtualNode, x: torch.Tensor) -> torch.Tensor:
+        return x.permute(0, 3, 1, 2) if vn.nhwc else x        # zero-copy logical NCHW view of the NHWC shard
+
     def _train_step(self, vn: VirtualNode, lr: float) -> None:
         pos = vn.step * vn.eb + vn.arange
         idx = vn.perm_buf.index_select(0, pos)
-        xb = vn.X.index_select(0, idx); yb = vn.y.index_select(0, idx)
+        xb = self._inputs(vn, vn.X.index_select(0, idx)); yb = vn.y.index_select(0, idx)
+        for p in vn.params:
+            p.grad = None                                      # autograd hands us its own grad buffers: no accumulate pass
         with self._autocast():
             out = vn.model(xb)
         loss = self._loss(out, yb)
         loss.backward()
-        self.ext.sgd_step(self.live, self.layout.stride, self.grad, self.layout.Pp4, vn.slot, 1, self.layout.Pp4, lr)
+        grads = []
+        for p in vn.params:
+            g = p.grad
+            if g.stride() != p.stride() or g.dtype != p.dtype:
+                g = torch.empty_like(p).copy_(g)
+            grads.append(g)
+        self.ext.sgd_multi(vn.params, grads, lr)              # one launch: θ -= lr·g for every tensor of the node
         vn.step += 1
         vn.loss_sum += loss.detach()
 
@@ -343,7 +360,7 @@ class B200Network:
             self._train_step(vn, lr)
         vn.train_graph = graph
         self.live[vn.slot].copy_(snap); self.ints[vn.slot].copy_(snap_i)
-        self.grad[vn.slot].zero_(); vn.step.zero_(); vn.loss_sum.zero_()
+        vn.step.zero_(); vn.loss_sum.zero_()
         torch.cuda.set_rng_state(rng, self.device)
 
     def _fork(self) -> None:
@@ -615,7 +632,7 @@ class B200Network:
             if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
                 continue
             pick = torch.randperm(vn.n, device=self.device)[: vn.eb]
-            xb, yb = vn.X.index_select(0, pick), vn.y.index_select(0, pick)
+            xb, yb = self._inputs(vn, vn.X.index_select(0, pick)), vn.y.index_select(0, pick)
             own_loss[vi] = F.cross_entropy(self._forward_with(vn, None, xb), yb)
             for e in range(rows[vi] + 1, rows[vi + 1]):
                 if cand_host[e] != 0:
@@ -642,7 +659,7 @@ class B200Network:
             order = torch.randperm(vn.n, device=self.device)
             nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
             take = order[: min(vn.n, nbatch * vn.eb)]
-            xb, yb = vn.X.index_select(0, take), vn.y.index_select(0, take)
+            xb, yb = self._inputs(vn, vn.X.index_select(0, take)), vn.y.index_select(0, take)
             for e in range(rows[vi] + 1, rows[vi + 1]):
                 alpha = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), xb)
                 self.ext.dirichlet_eval(alpha.contiguous(), yb, None, stats[e])
@@ -703,7 +720,7 @@ class B200Network:
         EB = max(1, self.opt.eval_batch)
         with torch.no_grad():
             for a in range(0, vn.n, EB):
-                xb, yb = vn.X[a:a + EB], vn.y[a:a + EB]
+                xb, yb = self._inputs(vn, vn.X[a:a + EB]), vn.y[a:a + EB]
                 with self._autocast():
                     out = vn.model(xb).float().contiguous()
                 if self.evidential:
@@ -810,7 +827,7 @@ class B200Network:
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
         for vi, vn in enumerate(self.nodes):
             for e in range(rows[vi] + 1, rows[vi + 1]):
-                out = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), vn.X)
+                out = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), self._inputs(vn, vn.X))
                 if self.evidential:
                     self.ext.dirichlet_eval(out.contiguous(), vn.y, None, stats[e])
                 else:

@@ -137,3 +137,33 @@ def test_leaf_partitions_and_json_loader(tmp_path):
     assert all(len(p) <= 4 for p in ad.get_client_partitions())
     syn = load_leaf_adapter("femnist", data_path="synthetic", num_nodes=2, samples_per_node=8)
     assert syn.client_tensors(0)[0].shape[1:] == (1, 28, 28)
+
+
+def test_state_layout_and_channels_last_permutation():
+    import torch.nn as nn
+    from murmura_b200.models import ResNet18, CIFARCNN
+    from murmura_b200.parallel.arena import Placement, StateLayout
+    m = ResNet18()
+    lay = StateLayout.from_model(m)
+    assert lay.P_float_real == 11191242 and lay.Pi == 20 and lay.Pp == 11181642
+    assert lay.Pf_pad % 256 == 0 and lay.stride == lay.Pf_pad + 256 and lay.Pp4 % 4 == 0
+    names = [e.name for e in lay.entries]
+    assert names.index("fc.bias") < names.index("bn1.running_mean") < names.index("bn1.num_batches_tracked")
+    small = CIFARCNN()
+    for cl in (False, True):
+        lay = StateLayout.from_model(small, channels_last=cl)
+        row = torch.zeros(lay.stride); ints = torch.zeros(max(lay.Pi, 1), dtype=torch.long)
+        ref_flat = torch.cat([t.flatten() for t in small.state_dict().values() if t.is_floating_point()])
+        lay.bind(small, row, None, ints if lay.Pi else None)
+        perm = lay.ref_permutation()
+        ok = perm >= 0
+        assert ok.sum() == lay.P_float_real and sorted(perm[ok].tolist()) == list(range(lay.P_float_real))
+        assert torch.equal(row[: lay.Pf][torch.from_numpy(ok)], ref_flat[torch.from_numpy(perm[ok])])
+        views = lay.row_views(row, None)
+        assert all(torch.equal(views[k], v) for k, v in small.state_dict().items())       # logical values unchanged
+        w = dict(small.named_parameters())["conv1.weight"]
+        assert w.data_ptr() == row.data_ptr() and w.is_contiguous(memory_format=torch.channels_last) == cl or not cl
+        assert small(torch.zeros(2, 3, 32, 32)).shape == (2, 10)
+    p = Placement(20, 8)
+    assert p.counts == [3, 3, 3, 3, 2, 2, 2, 2] and p.slots_per_rank == 3 and p.local_nodes(4) == [12, 13]
+    assert int(p.rank_of[13]) == 4 and int(p.slot_of[13]) == 1 and Placement(4, 8).counts == [1, 1, 1, 1, 0, 0, 0, 0]

@@ -438,3 +438,20 @@ def test_gram_tcgen05_tf32(ext, rows, P):
     d_ref = torch.cdist(sel, sel).pow(2).float()
     dg = got.diagonal()[:, None] + got.diagonal()[None, :] - 2 * got
     assert ((dg - d_ref).abs().max() / d_ref.max()).item() < 5e-3
+
+
+def test_sgd_multi(ext):
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 3, 7, 7), (10,), (512, 512, 3, 3), (5130,), (1,), (3, 5)]
+    params = [torch.randn(*s, generator=g).to(DEV) for s in shapes]
+    params[0] = params[0].contiguous(memory_format=torch.channels_last)
+    grads = [torch.randn_like(p) for p in params]                       # randn_like preserves the channels_last strides
+    assert grads[0].stride() == params[0].stride()
+    ref = [p - 0.05 * gr for p, gr in zip(params, grads)]
+    g0 = [gr.clone() for gr in grads]
+    ext.sgd_multi(params, grads, 0.05)
+    for p, r, gr, gr0 in zip(params, ref, grads, g0):
+        assert torch.allclose(p, r, atol=1e-6) and torch.equal(gr, gr0)
+    big = torch.zeros(22_000_000, device=DEV); gb = torch.ones_like(big)   # > 320 chunks → split across launches
+    ext.sgd_multi([big], [gb], 2.0)
+    assert (big == -2.0).all()
