@@ -51,8 +51,7 @@ __global__ void __launch_bounds__(kThreads) publish_kernel(PublishArgs a) {
     const int n4 = a.Pf_pad >> 2;
     const float sc = a.scale[v], sd = a.noise_std[v];
     const uint64_t stream = a.round * 1000003ull + (uint64_t)a.node_gid[v];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        float4 x = src[i];
+    auto transform = [&](float4 x, int i) {
         if (sc != 1.f) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
         if (sd != 0.f) {
             const float4 z = philox_normal4(a.seed, stream, (uint64_t)i);
@@ -62,8 +61,19 @@ __global__ void __launch_bounds__(kThreads) publish_kernel(PublishArgs a) {
             if (base + 2 < a.Pf) x.z = fmaf(sd, z.z, x.z);
             if (base + 3 < a.Pf) x.w = fmaf(sd, z.w, x.w);
         }
-        st_stream(dst + i, x);
+        return x;
+    };
+    constexpr int U = 4;                                   // independent 128-bit loads in flight per thread
+    const int step = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * step < n4; i += U * step) {
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = ld_stream(src + i + u * step);
+#pragma unroll
+        for (int u = 0; u < U; ++u) st_stream(dst + i + u * step, transform(x[u], i + u * step));
     }
+    for (; i < n4; i += step) st_stream(dst + i, transform(src[i], i));
     if (blockIdx.x == 0 && a.n_int > 0) {                  // int buffers ride along as floats (never attacked)
         float* lt = a.live + (size_t)v * a.stride + a.Pf_pad;
         float* pt = a.pub + (size_t)v * a.stride + a.Pf_pad;

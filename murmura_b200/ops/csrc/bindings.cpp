@@ -49,9 +49,10 @@ void ce_eval(Tensor logits, Tensor targets, c10::optional<Tensor> n_valid, Tenso
 void dirichlet_eval(Tensor alpha, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats);
 std::vector<Tensor> evidential_loss_fwd_bwd(Tensor alpha, Tensor targets, double lam, c10::optional<Tensor> lam_t);
 // gram_tcgen05.cu
-Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_stride, int64_t row_len, int64_t box_rows);
-void gram_tf32(Tensor maps_cpu, std::vector<int64_t> box_map, std::vector<int64_t> box_y, int64_t box_rows, int64_t kb0,
-               int64_t kb1, int64_t R, Tensor out, bool zero_out, int64_t max_ctas);
+Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_stride, int64_t row_len, int64_t kb_per_stage);
+int64_t gram_kb_per_stage(int64_t ngroups);
+void gram_tf32(Tensor maps_cpu, std::vector<int64_t> group_map, std::vector<int64_t> group_y, int64_t kb0, int64_t kb1,
+               int64_t R, Tensor out, bool zero_out, int64_t max_ctas);
 // dmtt.cu
 void mobility_adjacency(Tensor pos, int64_t round, double area, double range, bool ensure_connected, Tensor adj);
 void liar_claims(Tensor adj, Tensor is_liar, Tensor claims);
@@ -84,6 +85,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("evidential_loss_fwd_bwd", &evidential_loss_fwd_bwd);
     m.def("gram_tf32", &gram_tf32);
     m.def("gram_make_maps", &gram_make_maps);
+    m.def("gram_kb_per_stage", &gram_kb_per_stage);
     m.def("mobility_adjacency", &mobility_adjacency);
     m.def("liar_claims", &liar_claims);
     m.def("dmtt_update", &dmtt_update);

@@ -25,14 +25,18 @@ namespace mb {
 
 constexpr int kGramRows = 128;                 // UMMA M (tile rows; unused rows are ignored)
 constexpr int kGramKB = 32;                    // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int kGramStages = 6;
-constexpr int kStageBytes = kGramRows * kGramKB * 4;   // 16 KiB
-constexpr int kMaxBoxes = 16;
+constexpr int kMaxStages = 8;
+constexpr int kMaxGroups = 16;                 // 8-row groups per tile (16 × 8 = 128 rows)
 constexpr int kMaxMaps = 16;
 constexpr int kGramThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
 
+// The tile is assembled from 8-row groups; group g = rows [8g, 8g+8) comes from tensor map `map[g]` at row `y[g]`.
+// One TMA instruction fetches ONE group for `kb_per_stage` consecutive k-blocks (3-D box {32 floats, 8 rows, KB}),
+// landing as [KB][8 rows][128 B]; the stage is laid out [group][KB][8][128 B], so for a fixed k-block the 8-row
+// groups are a constant KB·1024 B apart — exactly the SBO of the UMMA shared-memory descriptor.
 struct GramMaps { CUtensorMap m[kMaxMaps]; };
-struct GramBoxes { int n; int rows; int map[kMaxBoxes]; int y[kMaxBoxes]; };
+struct GramGroups { int n; int kb_per_stage; int stages; int map[kMaxGroups]; int y[kMaxGroups]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -54,17 +58,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();        // never hang the GPU: a lost arrival aborts the kernel instead
     }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-// K-major operand, 128-byte swizzle: rows are 128 B, 8-row groups are 1024 B apart (SBO), descriptor version 1.
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+// K-major operand, 128-byte swizzle: rows are 128 B, 8-row groups are `sbo_bytes` apart, descriptor version 1.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address  [0,14)
     d |= (uint64_t)0 << 16;                                  // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset [32,46)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;       // stride byte offset [32,46)
     d |= (uint64_t)1 << 46;                                  // descriptor version (sm_100)
     d |= (uint64_t)2 << 61;                                  // layout: SWIZZLE_128B
     return d;
@@ -83,30 +87,33 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 __global__ void __launch_bounds__(kGramThreads, 1)
-gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramBoxes boxes, int kb0, int kb1, int n_mma, int R,
+gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramGroups grp, int kb0, int kb1, int n_mma, int R,
                  float* __restrict__ out /*[128][128]*/) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[kGramStages];
-    __shared__ __align__(8) uint64_t empty_bar[kGramStages];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // split-K: contiguous chunk of k-blocks per CTA
-    const int total = kb1 - kb0;
-    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int my0 = kb0 + (int)blockIdx.x * per;
-    const int my1 = min(kb1, my0 + per);
-    const int num_kb = max(0, my1 - my0);
+    const int KB = grp.kb_per_stage, NS = grp.stages;
+    const uint32_t group_bytes = (uint32_t)KB * 1024u;               // one group's slab inside a stage
+    const uint32_t stage_bytes = (uint32_t)grp.n * group_bytes;
+    // split-K: contiguous chunk of k-block *super-steps* (KB k-blocks each) per CTA
+    const int total_steps = (kb1 - kb0 + KB - 1) / KB;
+    const int per = (total_steps + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int s0 = (int)blockIdx.x * per;
+    const int s1 = min(total_steps, s0 + per);
+    const int num_steps = max(0, s1 - s0);
 
     if (warp == 0 && lane == 0) {
-        for (int b = 0; b < boxes.n; ++b)
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.m[boxes.map[b]]) : "memory");
+        for (int g = 0; g < grp.n; ++g)
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.m[grp.map[g]]) : "memory");
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kGramStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
             mbar_init(&accum_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -119,39 +126,42 @@ gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramBoxes boxes, i
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (num_kb > 0) {
+    if (num_steps > 0) {
         if (warp == 0) {
-            // ===== TMA producer =====
+            // ===== TMA producer: one 3-D bulk tensor load per 8-row group per stage =====
             if (lane == 0) {
-                const uint32_t stage_tx = (uint32_t)boxes.n * (uint32_t)boxes.rows * 128u;
                 int stage = 0; uint32_t phase = 0;
-                for (int kb = my0; kb < my1; ++kb) {
+                for (int st = s0; st < s1; ++st) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    mbar_expect_tx(&full_bar[stage], stage_tx);
-                    uint8_t* tile = smem + stage * kStageBytes;
-                    for (int b = 0; b < boxes.n; ++b)
-                        tma_load_2d(tile + b * boxes.rows * 128, &maps.m[boxes.map[b]], kb * kGramKB, boxes.y[b], &full_bar[stage]);
-                    if (++stage == kGramStages) { stage = 0; phase ^= 1u; }
+                    mbar_expect_tx(&full_bar[stage], stage_bytes);          // OOB k-blocks / rows are zero-filled and still counted
+                    uint8_t* tile = smem + (size_t)stage * stage_bytes;
+                    const int kb = kb0 + st * KB;
+                    for (int g = 0; g < grp.n; ++g)
+                        tma_load_3d(tile + (size_t)g * group_bytes, &maps.m[grp.map[g]], 0, grp.y[g], kb, &full_bar[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1u; }
                 }
             }
         } else if (warp == 1) {
-            // ===== MMA issuer (single elected lane) =====
+            // ===== MMA issuer (single elected lane): 4·KB tf32 MMAs per stage, A and B are the SAME smem tile =====
             if (lane == 0) {
                 const uint32_t idesc = make_tf32_idesc(kGramRows, n_mma);
                 int stage = 0; uint32_t phase = 0;
-                for (int kb = my0; kb < my1; ++kb) {
+                for (int st = s0; st < s1; ++st) {
                     mbar_wait(&full_bar[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t tile_addr = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t tile_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const int kb_here = min(KB, kb1 - (kb0 + st * KB));      // tail stage: skip zero-filled k-blocks
+                    for (int j = 0; j < kb_here; ++j) {
 #pragma unroll
-                    for (int k = 0; k < kGramKB / 8; ++k) {          // UMMA_K = 8 for tf32 → 32-byte steps inside the swizzle row
-                        const uint64_t desc = make_sw128_kmajor_desc(tile_addr + k * 32);
-                        umma_tf32(tmem_base, desc, desc, idesc, (kb > my0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kGramKB / 8; ++k) {              // UMMA_K = 8 (tf32) → 32-byte steps inside the swizzle row
+                            const uint64_t desc = make_sw128_kmajor_desc(tile_addr + j * 1024 + k * 32, group_bytes);
+                            umma_tf32(tmem_base, desc, desc, idesc, (st > s0 || j > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty_bar[stage]);                  // frees the smem slot once these MMAs retire
-                    if (++stage == kGramStages) { stage = 0; phase ^= 1u; }
+                    umma_commit(&empty_bar[stage]);                          // frees the smem slot once these MMAs retire
+                    if (++stage == NS) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&accum_bar);                             // accumulator complete
+                umma_commit(&accum_bar);                                     // accumulator complete
             }
         } else {
             // ===== epilogue: TMEM → registers → fp32 reductions into the global R×R tile =====
@@ -203,21 +213,22 @@ EncodeTiledFn get_encode() {
 }
 }  // namespace
 
-// One 2-D fp32 tensor map per source buffer: [rows][row_len] with `row_stride` elements between rows,
-// box = [box_rows][32 floats], 128-byte swizzle.  Returns a CPU byte tensor [nbuf][128].
-Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_stride, int64_t row_len, int64_t box_rows) {
+// One 3-D fp32 tensor map per source buffer [rows][row_len] (row_stride elements between rows), viewed as
+// {32 floats, rows, row_len/32}: box = {32, 8 rows, kb_per_stage k-blocks}, 128-byte swizzle.
+// Returns a CPU byte tensor [nbuf][128].
+Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_stride, int64_t row_len, int64_t kb_per_stage) {
     TORCH_CHECK((int)base_ptrs.size() <= mb::kMaxMaps, "at most ", mb::kMaxMaps, " source buffers");
-    TORCH_CHECK(box_rows % 8 == 0 && box_rows >= 8 && box_rows <= 128, "box_rows must be a multiple of 8 in [8,128]");
-    TORCH_CHECK(row_stride % 4 == 0, "row stride must be 16-byte aligned");
+    TORCH_CHECK(kb_per_stage >= 1 && kb_per_stage <= 16);
+    TORCH_CHECK(row_stride % 4 == 0 && row_len % 32 == 0, "row stride must be 16-byte aligned and row_len a multiple of 32");
     Tensor t = torch::zeros({(int64_t)base_ptrs.size(), (int64_t)sizeof(CUtensorMap)}, torch::kUInt8);
     auto enc = get_encode();
     for (size_t i = 0; i < base_ptrs.size(); ++i) {
-        cuuint64_t gdim[2] = {(cuuint64_t)row_len, (cuuint64_t)rows};
-        cuuint64_t gstride[1] = {(cuuint64_t)row_stride * 4};
-        cuuint32_t box[2] = {(cuuint32_t)mb::kGramKB, (cuuint32_t)box_rows};
-        cuuint32_t estr[2] = {1, 1};
+        cuuint64_t gdim[3] = {(cuuint64_t)mb::kGramKB, (cuuint64_t)rows, (cuuint64_t)(row_len / mb::kGramKB)};
+        cuuint64_t gstride[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)mb::kGramKB * 4};
+        cuuint32_t box[3] = {(cuuint32_t)mb::kGramKB, 8u, (cuuint32_t)kb_per_stage};
+        cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(reinterpret_cast<CUtensorMap*>(t.data_ptr<uint8_t>() + i * sizeof(CUtensorMap)),
-                         CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(base_ptrs[i]), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, reinterpret_cast<void*>(base_ptrs[i]), gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", (int)r);
@@ -225,34 +236,62 @@ Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_
     return t;
 }
 
-// out[128*128] (+)= Gram of the tile rows assembled from `boxes` over k-blocks [kb0, kb1) (32 floats each).
-void gram_tf32(Tensor maps_cpu, std::vector<int64_t> box_map, std::vector<int64_t> box_y, int64_t box_rows, int64_t kb0,
-               int64_t kb1, int64_t R, Tensor out, bool zero_out, int64_t max_ctas) {
+// Stage geometry shared by the host wrappers: k-blocks per TMA instruction and pipeline depth for `ngroups` groups.
+// UMMA M is fixed at 128 rows = 16 groups, so the A operand of the LAST stage reads up to 16 group slabs past its
+// start: the allocation carries (16 - ngroups) slabs of padding after the last stage (rows >= R are never read back).
+static int64_t gram_smem_bytes(int ngroups, int kb, int stages) {
+    return ((int64_t)stages * ngroups + (mb::kMaxGroups - ngroups)) * kb * 1024 + 1024;
+}
+static void gram_geometry(int ngroups, int* kb_per_stage, int* stages) {
+    int best_kb = 1, best_st = 2; int64_t best_inflight = 0;
+    for (int kb = 8; kb >= 1; kb >>= 1) {
+        const int64_t avail = mb::kSmemBudget - (int64_t)(mb::kMaxGroups - ngroups) * kb * 1024;
+        int st = (int)std::min<int64_t>(mb::kMaxStages, avail / ((int64_t)ngroups * kb * 1024));
+        if (st < 2) continue;
+        if (st >= 4) { best_kb = kb; best_st = st; break; }             // deep enough: take the largest TMA box
+        const int64_t inflight = (int64_t)st * ngroups * kb * 1024;
+        if (inflight > best_inflight) { best_inflight = inflight; best_kb = kb; best_st = st; }
+    }
+    *kb_per_stage = best_kb;
+    *stages = best_st;
+}
+
+int64_t gram_kb_per_stage(int64_t ngroups) {
+    int kb, st;
+    gram_geometry((int)ngroups, &kb, &st);
+    return kb;
+}
+
+// out[128*128] (+)= Gram of the tile rows (8-row groups `group_map`/`group_y`) over k-blocks [kb0, kb1) (32 floats each).
+void gram_tf32(Tensor maps_cpu, std::vector<int64_t> group_map, std::vector<int64_t> group_y, int64_t kb0, int64_t kb1,
+               int64_t R, Tensor out, bool zero_out, int64_t max_ctas) {
     c10::cuda::CUDAGuard guard(out.device());
     TORCH_CHECK(out.numel() == mb::kGramRows * mb::kGramRows && out.dtype() == torch::kFloat32 && out.is_contiguous());
-    TORCH_CHECK(box_map.size() == box_y.size() && (int)box_map.size() <= mb::kMaxBoxes && !box_map.empty());
-    const int rows_total = (int)(box_map.size() * box_rows);
-    TORCH_CHECK(rows_total <= mb::kGramRows, "tile holds at most 128 rows");
+    TORCH_CHECK(group_map.size() == group_y.size() && (int)group_map.size() <= mb::kMaxGroups && !group_map.empty());
+    const int ngroups = (int)group_map.size();
+    const int rows_total = ngroups * 8;
     TORCH_CHECK(R <= rows_total);
     mb::GramMaps maps;
     memset(&maps, 0, sizeof(maps));
     memcpy(&maps, maps_cpu.data_ptr<uint8_t>(), (size_t)maps_cpu.numel());
-    mb::GramBoxes boxes;
-    boxes.n = (int)box_map.size(); boxes.rows = (int)box_rows;
-    for (int b = 0; b < boxes.n; ++b) { boxes.map[b] = (int)box_map[b]; boxes.y[b] = (int)box_y[b]; }
+    mb::GramGroups grp;
+    grp.n = ngroups;
+    gram_geometry(ngroups, &grp.kb_per_stage, &grp.stages);
+    for (int g = 0; g < ngroups; ++g) { grp.map[g] = (int)group_map[g]; grp.y[g] = (int)group_y[g]; }
     const int n_mma = std::max(16, (rows_total + 15) / 16 * 16);
     auto stream = at::cuda::getCurrentCUDAStream();
     if (zero_out) cudaMemsetAsync(out.data_ptr<float>(), 0, out.numel() * sizeof(float), stream);
     if (kb1 <= kb0) return;
-    const int smem = mb::kGramStages * mb::kStageBytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    const int smem = (int)gram_smem_bytes(ngroups, grp.kb_per_stage, grp.stages);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
         cudaFuncSetAttribute(mb::gram_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
+        attr_smem = smem;
     }
     int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
     if (max_ctas > 0) sms = std::min<int>(sms, (int)max_ctas);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (kb1 - kb0 + 7) / 8));   // >= 8 k-blocks per CTA
-    mb::gram_tf32_kernel<<<grid, mb::kGramThreads, smem, stream>>>(maps, boxes, (int)kb0, (int)kb1, n_mma, (int)R, out.data_ptr<float>());
+    const int64_t steps = (kb1 - kb0 + grp.kb_per_stage - 1) / grp.kb_per_stage;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (steps + 3) / 4));      // >= 4 super-steps per CTA
+    mb::gram_tf32_kernel<<<grid, mb::kGramThreads, smem, stream>>>(maps, grp, (int)kb0, (int)kb1, n_mma, (int)R, out.data_ptr<float>());
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ live,
 // Gradients stay wherever autograd produced them (no accumulate-into-arena pass); pointers travel in the kernel
 // parameter block, so the launch is CUDA-graph capturable with zero device-side tables.
 constexpr int kMtTensors = 64;
-constexpr int kMtBlocks = 320;
-constexpr int kMtChunk = 65536;                   // floats per block
+constexpr int kMtBlocks = 1024;                   // (kernel parameter block: ~6.4 KiB, limit 32 KiB since CUDA 12.1)
+constexpr int kMtChunk = 16384;                   // floats per block → ResNet-18 = 690 blocks ≈ 4.7 per SM
 struct MultiSgdArgs {
     float* p[kMtTensors];
     const float* g[kMtTensors];

@@ -547,20 +547,23 @@ class B200Network:
         if "gram_plan" in et:
             return et["gram_plan"]
         S, G, L = self.S, self.world, self.layout
-        box = (S + 7) // 8 * 8
+        gpr = (S + 7) // 8                              # 8-row groups per plane per rank
+        ngroups = 2 * G * gpr
         plan = None
-        if 2 * G * box <= 128 and et["max_m"] <= 32:
-            row_of_live = lambda r, s: (2 * r) * box + s
-            row_of_pub = lambda r, s: (2 * r + 1) * box + s
+        if ngroups <= 16 and et["max_m"] <= 32:
+            row_of_live = lambda r, s: (2 * r * gpr + s // 8) * 8 + s % 8
+            row_of_pub = lambda r, s: ((2 * r + 1) * gpr + s // 8) * 8 + s % 8
             idx = torch.zeros(max(self.V, 1), 32, dtype=torch.int64)
             rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
             for vi, vn in enumerate(self.nodes):
                 for c, e in enumerate(range(rows[vi], rows[vi + 1])):
                     idx[vi, c] = row_of_live(self.rank, vn.slot) if c == 0 else row_of_pub(rk[e], sl[e])
-            maps = self.ext.gram_make_maps([self.arena.base_ptr(r) for r in range(G)], 3 * S, L.stride, L.Pf_pad, box)
+            kbs = int(self.ext.gram_kb_per_stage(ngroups))
+            maps = self.ext.gram_make_maps([self.arena.base_ptr(r) for r in range(G)], 3 * S, L.stride, L.Pf_pad, kbs)
             nkb = L.Pf_pad // 32
             lo, hi = nkb * self.rank // G, nkb * (self.rank + 1) // G
-            plan = {"maps": maps, "box": box, "idx": idx.to(self.device), "kb": (lo, hi), "R": 2 * G * box,
+            lo, hi = lo // kbs * kbs, (hi // kbs * kbs if self.rank + 1 < G else nkb)      # stage-aligned K shards
+            plan = {"maps": maps, "gpr": gpr, "idx": idx.to(self.device), "kb": (lo, hi), "R": ngroups * 8,
                     "out": torch.zeros(128 * 128, device=self.device)}
         et["gram_plan"] = plan
         return plan
@@ -573,11 +576,14 @@ class B200Network:
         if plan is not None:
             if self.world > 1:
                 self._host_wait_epoch()
-            S, box = self.S, plan["box"]
-            box_map, box_y = [], []
-            for r in range(self.world):
-                box_map += [r, r]; box_y += [0, (1 + parity) * S]
-            self.ext.gram_tf32(plan["maps"], box_map, box_y, box, plan["kb"][0], plan["kb"][1], plan["R"], plan["out"], True, 0)
+            S, gpr = self.S, plan["gpr"]
+            group_map, group_y = [], []
+            for r in range(self.world):                   # per rank: live-plane groups, then published[parity] groups
+                for j in range(gpr):
+                    group_map.append(r); group_y.append(8 * j)
+                for j in range(gpr):
+                    group_map.append(r); group_y.append((1 + parity) * S + 8 * j)
+            self.ext.gram_tf32(plan["maps"], group_map, group_y, plan["kb"][0], plan["kb"][1], plan["R"], plan["out"], True, 0)
             self.kernel_launches += 2
             Gm = plan["out"].view(128, 128)
             if self.world > 1:

@@ -409,36 +409,48 @@ def test_mobility_and_dmtt_kernels(ext):
                 assert q[v, j].item() == pytest.approx(st.collab_score(j, ms.get(j, 0.5)), rel=1e-4, abs=1e-5)
 
 
-@pytest.mark.parametrize("rows,P", [(8, 4096), (24, 100000 // 32 * 32), (48, 1 << 20)])
+@pytest.mark.parametrize("rows,P", [(8, 4096), (24, 100000 // 32 * 32), (48, 1 << 20), (20, 11191296)])
 def test_gram_tcgen05_tf32(ext, rows, P):
     """tcgen05/TMEM/TMA Gram kernel vs an fp64 X·Xᵀ (TF32 inputs → ~1e-3 relative)."""
     g = torch.Generator().manual_seed(rows)
     stride = P + 256
     X = torch.zeros(3 * rows, stride, device=DEV)
     X[:, :P] = torch.randn(3 * rows, P, generator=g).to(DEV)
-    box = (rows + 7) // 8 * 8
-    maps = ext.gram_make_maps([X.data_ptr()], 3 * rows, stride, P, box)
+    gpr = (rows + 7) // 8
+    # tile = 8-row groups of rows [0, rows) ("live" plane) followed by groups of [2*rows, 3*rows) ("published parity 1")
+    gy = [8 * j for j in range(gpr)] + [2 * rows + 8 * j for j in range(gpr)]
+    gm = [0] * len(gy)
+    kbs = ext.gram_kb_per_stage(len(gy))
+    maps = ext.gram_make_maps([X.data_ptr()], 3 * rows, stride, P, kbs)
     out = torch.zeros(128 * 128, device=DEV)
-    # tile = [rows 0..rows) ("live" plane)  +  [rows 2*rows..3*rows) ("published parity 1" plane)
-    ext.gram_tf32(maps, [0, 0], [0, 2 * rows], box, 0, P // 32, 2 * box, out, True, 0)
+    R = 8 * len(gy)
+    ext.gram_tf32(maps, gm, gy, 0, P // 32, R, out, True, 0)
     torch.cuda.synchronize()
     G = out.view(128, 128)
-    sel = torch.cat([X[:box, :P], X[2 * rows:2 * rows + box, :P]]).double()
+    sel_rows = [min(y + i, 3 * rows - 1) for y in gy for i in range(8)]
+    valid = torch.tensor([y + i < 3 * rows for y in gy for i in range(8)])
+    sel = X[sel_rows, :P].double() * valid.to(DEV).double().unsqueeze(1)         # rows past the tensor end are zero-filled by TMA
     ref = (sel @ sel.T).float()
-    got = G[:2 * box, :2 * box]
+    got = G[:R, :R]
     err = (got - ref).abs().max().item() / ref.diagonal().max().item()
     assert err < 3e-3, err
-    # split-K accumulation across two launches equals one launch
+    # split-K accumulation across two launches (stage-aligned split) equals one launch
     out2 = torch.zeros(128 * 128, device=DEV)
-    half = (P // 32) // 2
-    ext.gram_tf32(maps, [0, 0], [0, 2 * rows], box, 0, half, 2 * box, out2, True, 0)
-    ext.gram_tf32(maps, [0, 0], [0, 2 * rows], box, half, P // 32, 2 * box, out2, False, 0)
-    assert torch.allclose(out2.view(128, 128)[:2 * box, :2 * box], got, rtol=1e-3, atol=1e-2 * ref.diagonal().max().item() * 1e-2)
+    half = (P // 32) // 2 // kbs * kbs
+    ext.gram_tf32(maps, gm, gy, 0, half, R, out2, True, 0)
+    ext.gram_tf32(maps, gm, gy, half, P // 32, R, out2, False, 0)
+    scale = ref.diagonal().max().item()
+    assert ((out2.view(128, 128)[:R, :R] - got).abs().max().item() / scale) < 1e-3
+    # an unaligned tail (kb1 not a multiple of the stage depth) only accumulates the valid k-blocks
+    out3 = torch.zeros(128 * 128, device=DEV)
+    kb_tail = max(1, P // 32 - 3)
+    ext.gram_tf32(maps, gm, gy, 0, kb_tail, R, out3, True, 0)
+    ref3 = (sel[:, :kb_tail * 32] @ sel[:, :kb_tail * 32].T).float()
+    assert ((out3.view(128, 128)[:R, :R] - ref3).abs().max().item() / scale) < 3e-3
     # distances from the Gram agree with exact fp32 distances to TF32 accuracy
     d_ref = torch.cdist(sel, sel).pow(2).float()
     dg = got.diagonal()[:, None] + got.diagonal()[None, :] - 2 * got
     assert ((dg - d_ref).abs().max() / d_ref.max()).item() < 5e-3
-
 
 def test_sgd_multi(ext):
     g = torch.Generator().manual_seed(9)
