@@ -53,6 +53,7 @@ class StateLayout:
     Pi: int = 0           # int-buffer elements
     stride: int = 0       # elements per row
     P_float_real: int = 0  # number of float state elements (reference's "model_dim")
+    key_order: List[str] = field(default_factory=list)   # state_dict key order (what the reference flattens in)
 
     @classmethod
     def from_model(cls, model: nn.Module, channels_last: bool = False) -> "StateLayout":
@@ -66,6 +67,7 @@ class StateLayout:
                 ref_offsets[name] = ref_off
                 ref_off += t.numel()
         lay.P_float_real = ref_off
+        lay.key_order = list(state.keys())
         off = 0
         for name, t in state.items():
             if name in param_names:
@@ -98,15 +100,16 @@ class StateLayout:
         return [e for e in self.entries if e.kind == "int"]
 
     def row_views(self, row: torch.Tensor, ints: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """state-dict-shaped views of one arena row (+ optional int64 table row)."""
-        out: Dict[str, torch.Tensor] = {}
+        """state-dict-shaped views of one arena row (+ optional int64 table row), in ``state_dict`` key order
+        (aggregators that flatten a state — Sketchguard — depend on that order)."""
+        found: Dict[str, torch.Tensor] = {}
         for e in self.entries:
             if e.kind == "int":
                 if ints is not None:
-                    out[e.name] = ints[e.offset:e.offset + e.numel].view(e.shape)
+                    found[e.name] = ints[e.offset:e.offset + e.numel].view(e.shape)
             else:
-                out[e.name] = e.view(row)
-        return out
+                found[e.name] = e.view(row)
+        return {k: found[k] for k in self.key_order if k in found}
 
     def ref_permutation(self) -> np.ndarray:
         """``perm[arena_pos] = reference flatten index`` for real float elements, -1 for padding."""

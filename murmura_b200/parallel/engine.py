@@ -714,6 +714,7 @@ class B200Network:
         if self.dmtt_on:
             self._dmtt_score_and_update(et, parity)
         plan = getattr(self, f"_agg_{self.family}", self._agg_generic)
+        self._last_et = et
         plan(et, parity)
 
     # =========================================================================================

@@ -82,7 +82,12 @@ def check(algo, params, n, topo, b200=None, attack=ATTACK, rounds=2):
                     err = (gk.float() - w.float()).abs().max().item()
                     worst = max(worst, err)
                     if err > 5e-5 * max(1.0, w.abs().max().item()):
-                        raise AssertionError(f"[{algo}] rank {rank} node {vn.gid} key {k} round {r}: max err {err}")
+                        et = net._last_et; vi = vn.slot; e0, e1 = et["host_rows"][vi], et["host_rows"][vi + 1]
+                        dbg = {"gids": et["host_gid"][e0:e1], "w": et["w"][e0:e1].tolist(), "dist": et["dist"][e0:e1].tolist(),
+                               "stats": et["stats"][vi].tolist(), "cpu_thr": getattr(cpu_aggs[vn.gid], "threshold_history", [None])[-1:],
+                               "cpu_scores": {j: v[-1] for j, v in getattr(cpu_aggs[vn.gid], "neighbor_scores", {}).items()},
+                               "byz": sorted(net.compromised)}
+                        raise AssertionError(f"[{algo}] rank {rank} node {vn.gid} key {k} round {r}: max err {err}\n  debug: {dbg}")
                 elif not torch.equal(gk.long(), w.long()):
                     raise AssertionError(f"[{algo}] rank {rank} node {vn.gid} int key {k}: {gk} vs {w}")
     net.close()
@@ -112,7 +117,13 @@ def train_check():
 def main():
     init_distributed()
     G = dist.get_world_size()
-    n = max(6, 3 * G)
+    n = int(os.environ.get("MP_NODES", max(6, 3 * G)))
+    only = os.environ.get("MP_ONLY")
+    if only == "sketch":
+        kreg = {"type": "k-regular", "num_nodes": n, "k": 4}
+        check("sketchguard", {"sketch_size": 256, "gamma": 0.6, "alpha": 0.5}, n, kreg)
+        check("sketchguard", {"sketch_size": 256, "gamma": 0.6, "alpha": 0.5}, n, kreg, b200={"sketch_dtype": "fp8"})
+        dist.barrier(); dist.destroy_process_group(); return
     kreg = {"type": "k-regular", "num_nodes": n, "k": 4}
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n})
     check("fedavg", {}, n, {"type": "ring", "num_nodes": n})
