@@ -58,6 +58,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();        // never hang the GPU: a lost arrival aborts the kernel instead
     }
 }
+// Long wait (epilogue warps idle for the whole main loop): back off so the pollers do not steal issue slots
+// from the TMA / MMA warps that share their SM sub-partitions.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
@@ -165,7 +179,7 @@ gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramGroups grp, in
             }
         } else {
             // ===== epilogue: TMEM → registers → fp32 reductions into the global R×R tile =====
-            mbar_wait(&accum_bar, 0);
+            mbar_wait_backoff(&accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int q = warp & 3;                                  // TMEM lane quarter this warp may access
             const int row = q * 32 + lane;
