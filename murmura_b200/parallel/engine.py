@@ -86,6 +86,59 @@ class VirtualNode:
     graph_key: Any = None
 
 
+class ForeignEval:
+    """Score a *foreign* weight row on one node's data (UBAR stage 2, EvidentialTrust, DMTT model scores).
+
+    The reference deep-copies / ``load_state_dict``s a model per neighbour (``aggregation/ubar.py:170-190``,
+    ``aggregation/evidential_trust.py:236-281``, ``dmtt/node_process.py:309-363``).  Here the candidate row is pulled with ONE
+    device-to-device copy (over NVLink when it lives on a peer) into a per-node staging row whose views are the functional
+    state of the node's module, and the whole forward + metric kernel is ONE CUDA-graph replay: 3 launches per candidate.
+    """
+
+    def __init__(self, eng: "B200Network", vn: "VirtualNode", rows: int, kind: str):
+        L = eng.layout
+        self.eng, self.vn, self.kind, self.rows = eng, vn, kind, rows
+        self.stage = torch.zeros(L.stride, device=eng.device)
+        self.state = dict(L.row_views(self.stage, None))
+        for e in L.int_entries():
+            self.state[e.name] = eng.ints[vn.slot][e.offset:e.offset + e.numel].view(e.shape)
+        self.x = torch.zeros(rows, *vn.X.shape[1:], device=eng.device)
+        self.y = torch.zeros(rows, dtype=torch.long, device=eng.device)
+        self.stats = torch.zeros(_STAT_COLS, device=eng.device)
+        self.graph = None
+
+    def load_inputs(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        self.x.copy_(x); self.y.copy_(y)
+
+    def _body(self) -> None:
+        eng, vn = self.eng, self.vn
+        self.stats.zero_()
+        out = eng._forward_with(vn, self.state, eng._inputs(vn, self.x)).contiguous()
+        if self.kind == "dirichlet":
+            eng.ext.dirichlet_eval(out, self.y, None, self.stats)
+        else:
+            eng.ext.ce_eval(out, self.y, None, self.stats)
+
+    def run(self, src_row: torch.Tensor, out_stats: torch.Tensor) -> None:
+        n = self.eng.layout.Pf_pad
+        self.stage[:n].copy_(src_row[:n], non_blocking=True)
+        if self.eng.opt.cuda_graphs:
+            if self.graph is None:
+                side = self.eng.capture_streams[self.vn.slot % len(self.eng.capture_streams)]
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._body()
+                torch.cuda.current_stream().wait_stream(side)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    self._body()
+            self.graph.replay()
+        else:
+            self._body()
+        out_stats.copy_(self.stats, non_blocking=True)
+        self.eng.kernel_launches += 1
+
+
 class B200Network:
     """Blackwell-native counterpart of ``Network`` (same ``train``/``history`` contract)."""
 
@@ -201,6 +254,8 @@ class B200Network:
         self.epoch = 0
         self._lr = None
         self._edge_cache: Dict[Any, Dict[str, torch.Tensor]] = {}
+        self._evaluators: Dict[Any, ForeignEval] = {}
+        self._row_cache: Dict[Any, torch.Tensor] = {}
         self._stat_log: List[torch.Tensor] = []
         self._agg_state: Dict[str, torch.Tensor] = {}
         self.timers: Dict[str, float] = {"train_ms": 0.0, "aggregate_ms": 0.0, "eval_ms": 0.0, "rounds": 0}
@@ -623,6 +678,20 @@ class B200Network:
                 return vn.model(xb).float()
             return torch.func.functional_call(vn.model, state, (xb,)).float()
 
+    def _evaluator(self, vn: VirtualNode, rows: int, kind: str) -> ForeignEval:
+        key = (vn.slot, rows, kind)
+        ev = self._evaluators.get(key)
+        if ev is None:
+            ev = self._evaluators[key] = ForeignEval(self, vn, rows, kind)
+        return ev
+
+    def _src_row(self, rank: int, parity: int, slot: int) -> torch.Tensor:
+        key = (rank, parity, slot)
+        row = self._row_cache.get(key)
+        if row is None:
+            row = self._row_cache[key] = self.arena.peer_row(rank, parity, slot)
+        return row
+
     # ---- UBAR --------------------------------------------------------------------------------
     def _agg_ubar(self, et, parity: int) -> None:
         a = self.aggregator
@@ -633,16 +702,23 @@ class B200Network:
         self.kernel_launches += 1
         cand_host = cand.cpu()                                       # tiny D2H: which candidates to evaluate
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
-        loss.zero_()
+        stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        self._fork()
         for vi, vn in enumerate(self.nodes):
             if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
                 continue
-            pick = torch.randperm(vn.n, device=self.device)[: vn.eb]
-            xb, yb = self._inputs(vn, vn.X.index_select(0, pick)), vn.y.index_select(0, pick)
-            own_loss[vi] = F.cross_entropy(self._forward_with(vn, None, xb), yb)
-            for e in range(rows[vi] + 1, rows[vi + 1]):
-                if cand_host[e] != 0:
-                    loss[e] = F.cross_entropy(self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), xb), yb)
+            with torch.cuda.stream(self.streams[vi % len(self.streams)]):
+                ev = self._evaluator(vn, vn.eb, "ce")            # CrossEntropyLoss on raw outputs even for evidential models
+                pick = torch.randperm(vn.n, device=self.device)[: vn.eb]
+                ev.load_inputs(vn.X.index_select(0, pick), vn.y.index_select(0, pick))
+                ev.run(self.live[vn.slot], stats[rows[vi]])       # own loss (self edge slot)
+                for e in range(rows[vi] + 1, rows[vi + 1]):
+                    if cand_host[e] != 0:
+                        ev.run(self._src_row(rk[e], parity, sl[e]), stats[e])
+        self._join()
+        mean_loss = stats[:, 0] / stats[:, 2].clamp_min(1.0)
+        loss.copy_(mean_loss[: loss.numel()])
+        own_loss[: self.V] = mean_loss[torch.tensor(rows[: self.V], device=self.device)] if self.V else own_loss[: self.V]
         self.ext.ubar_stage2(*self._et_args(et), cand, rank_t, loss, own_loss, a.alpha, True)
         self.kernel_launches += 1
         self._log_stats(et)
@@ -659,16 +735,19 @@ class B200Network:
         vac, acc, trust = et["aux"], et["aux2"], et["aux3"]
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        self._fork()
         for vi, vn in enumerate(self.nodes):
             if vn.n == 0:
                 continue
-            order = torch.randperm(vn.n, device=self.device)
-            nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
-            take = order[: min(vn.n, nbatch * vn.eb)]
-            xb, yb = self._inputs(vn, vn.X.index_select(0, take)), vn.y.index_select(0, take)
-            for e in range(rows[vi] + 1, rows[vi + 1]):
-                alpha = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), xb)
-                self.ext.dirichlet_eval(alpha.contiguous(), yb, None, stats[e])
+            with torch.cuda.stream(self.streams[vi % len(self.streams)]):
+                nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
+                take_n = min(vn.n, nbatch * vn.eb)
+                ev = self._evaluator(vn, take_n, "dirichlet")
+                take = torch.randperm(vn.n, device=self.device)[:take_n]
+                ev.load_inputs(vn.X.index_select(0, take), vn.y.index_select(0, take))
+                for e in range(rows[vi] + 1, rows[vi + 1]):
+                    ev.run(self._src_row(rk[e], parity, sl[e]), stats[e])
+        self._join()
         cnt = stats[:, 2].clamp_min(1.0)
         vac.copy_((stats[:, 3] / cnt)[: vac.numel()]); acc.copy_((stats[:, 1] / cnt)[: acc.numel()])
         self.ext.trust_filter(*self._et_args(et), vac, acc, et["src_gid"], self.N, self._agg_state["ema"],
@@ -703,8 +782,77 @@ class B200Network:
             for k, v in st.items():
                 views[k].copy_(v.to(views[k].dtype))
 
+    # ---- NCCL + stock-PyTorch baseline (b200.transport: nccl) -----------------------------------------
+    def _aggregate_nccl(self, neighbors: List[List[int]]) -> None:
+        """The comparison baseline named in BASELINE.json: same placement and training, but the neighbour exchange is
+        ``torch.distributed`` NCCL send/recv along the edge list and the aggregation is the reference-parity aggregator
+        classes running stock PyTorch ops on the received state dicts (one aggregator instance per node, ``.item()``
+        syncs and all).  None of the fused kernels run on this path."""
+        L, pl = self.layout, self.placement
+        if not hasattr(self, "_nccl_aggs"):
+            self._nccl_aggs = {vn.gid: copy_aggregator(self.aggregator) for vn in self.nodes}
+        # 1. published copies (attack applied with torch ops)
+        pub_rows: Dict[int, torch.Tensor] = {}
+        pub_ints: Dict[int, torch.Tensor] = {}
+        for vn in self.nodes:
+            row = self.live[vn.slot].clone()
+            ints = self.ints[vn.slot].clone()
+            if vn.byzantine and self.attack is not None:
+                state = self.attack.apply_attack(node_id=vn.gid, model_state=dict(L.row_views(row, ints)), round_num=self.round_idx)
+                fresh = torch.zeros_like(row)
+                for k, v in L.row_views(fresh, None).items():
+                    v.copy_(state[k])
+                row = fresh
+            pub_rows[vn.gid], pub_ints[vn.gid] = row, ints
+        # 2. exchange along directed edges that cross ranks
+        recv_rows: Dict[Tuple[int, int], torch.Tensor] = {}
+        ops = []
+        dist = _dist() if self.world > 1 else None
+        order = [(j, i) for i in range(self.N) for j in neighbors[i] if pl.rank_of[i] != pl.rank_of[j]]   # (src, dst), same on all ranks
+        for src, dst in order:
+            rs, rd = int(pl.rank_of[src]), int(pl.rank_of[dst])
+            if rs == self.rank:
+                payload = torch.cat([pub_rows[src][: L.Pf_pad], pub_ints[src].float()])
+                ops.append(dist.P2POp(dist.isend, payload, rd))
+            elif rd == self.rank:
+                buf = torch.empty(L.Pf_pad + self.ints.shape[1], device=self.device)
+                recv_rows[(src, dst)] = buf
+                ops.append(dist.P2POp(dist.irecv, buf, rs))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        # 3. per-node aggregation with the stock classes on GPU tensors
+        results = []
+        for vn in self.nodes:
+            own = {k: v.clone() for k, v in L.row_views(self.live[vn.slot], self.ints[vn.slot]).items()}
+            nbrs = {}
+            for j in neighbors[vn.gid]:
+                if pl.rank_of[j] == self.rank:
+                    row, ints = pub_rows[j], pub_ints[j]
+                else:
+                    buf = recv_rows[(j, vn.gid)]
+                    row = torch.zeros(L.stride, device=self.device); row[: L.Pf_pad] = buf[: L.Pf_pad]
+                    ints = buf[L.Pf_pad:].round().long()
+                nbrs[j] = dict(L.row_views(row, ints if L.Pi else None))
+            loader = [(self._inputs(vn, vn.X[: max(vn.eb, 100)]), vn.y[: max(vn.eb, 100)])]
+            results.append(self._nccl_aggs[vn.gid].aggregate(node_id=vn.gid, own_state=own, neighbor_states=nbrs,
+                                                             round_num=self.round_idx, train_loader=loader,
+                                                             model_template=vn.model, device=self.device))
+        for vn, st in zip(self.nodes, results):
+            views = L.row_views(self.live[vn.slot], self.ints[vn.slot])
+            for k, v in st.items():
+                views[k].copy_(v.to(views[k].dtype))
+
     def _aggregate(self, parity: int) -> None:
         neighbors, key = self._neighbors_for_round(self.round_idx)
+        if self.opt.transport == "nccl":
+            if self.dmtt_on:                       # trust bookkeeping is shared; only exchange+aggregation differ
+                et = self._edge_table(neighbors, key)
+                if self.world > 1:
+                    self.arena.timed_out.zero_()
+                self._publish(parity)
+                self._dmtt_score_and_update(et, parity)
+            return self._aggregate_nccl(neighbors)
         et = self._edge_table(neighbors, key)
         if self.opt.fault_drop_edges:
             self._apply_fault_mask(et, self.round_idx)
@@ -832,13 +980,17 @@ class B200Network:
         received = torch.zeros(V, N, dtype=torch.uint8, device=self.device)
         rows, rk, sl, gids = et["host_rows"], et["host_rank"], et["host_slot"], et["host_gid"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        self._fork()
         for vi, vn in enumerate(self.nodes):
-            for e in range(rows[vi] + 1, rows[vi + 1]):
-                out = self._forward_with(vn, self._foreign_state(rk[e], parity, sl[e], vn), self._inputs(vn, vn.X))
-                if self.evidential:
-                    self.ext.dirichlet_eval(out.contiguous(), vn.y, None, stats[e])
-                else:
-                    self.ext.ce_eval(out.contiguous(), vn.y, None, stats[e])
+            if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1:
+                continue
+            with torch.cuda.stream(self.streams[vi % len(self.streams)]):
+                ev = self._evaluator(vn, vn.n, "dirichlet" if self.evidential else "ce")
+                if not getattr(ev, "_full_loaded", False):
+                    ev.load_inputs(vn.X, vn.y); ev._full_loaded = not bool(self._host_shards)
+                for e in range(rows[vi] + 1, rows[vi + 1]):
+                    ev.run(self._src_row(rk[e], parity, sl[e]), stats[e])
+        self._join()
         cnt = stats[:, 2].clamp_min(1.0)
         acc_e = stats[:, 1] / cnt
         u_e = stats[:, 3] / cnt if self.evidential else torch.zeros_like(acc_e)
@@ -976,6 +1128,11 @@ class B200Network:
         if self.world > 1:
             _dist().barrier()
         self.arena.close()
+
+
+def copy_aggregator(agg):
+    import copy
+    return copy.deepcopy(agg)
 
 
 def _ceil4(x: int) -> int:
