@@ -191,3 +191,25 @@ def test_zmq_dmtt_backend(tmp_path):
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=230)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "ROUNDS [1, 2]" in res.stdout
+
+
+def test_experiment_harness(tmp_path):
+    """Config generator + resumable suite runner that scrapes the stdout contract."""
+    import json
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    gen = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "generate_configs.py"), "--out", str(tmp_path / "cfgs"),
+                          "--backend", "simulation", "--rounds", "2"], capture_output=True, text=True, env=env)
+    assert gen.returncode == 0 and "wrote" in gen.stdout
+    files = sorted(os.listdir(tmp_path / "cfgs"))
+    assert len(files) > 100 and all(load_config(tmp_path / "cfgs" / f) for f in files[:5])
+    one = tmp_path / "one"; one.mkdir()
+    (one / "a.yaml").write_text((tmp_path / "cfgs" / "ppg_dalia__fedavg__none0__ring__a0.5.yaml").read_text())
+    res = tmp_path / "res.json"
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "run_suite.py"), str(one), "--results", str(res), "--device", "cpu"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert run.returncode == 0, run.stderr[-1000:]
+    rec = json.load(open(res))["a"]
+    assert rec["status"] == "ok" and len(rec["rounds"]) == 2 and "vacuity" in rec["rounds"][-1]
+    again = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "run_suite.py"), str(one), "--results", str(res), "--device", "cpu"],
+                           capture_output=True, text=True, env=env, timeout=300)
+    assert "1/1 experiments have results" in again.stdout and "ok " not in again.stdout.split("1/1")[0]      # resumed: nothing re-run
