@@ -128,4 +128,30 @@ def evidential_loss(alpha: torch.Tensor, targets: torch.Tensor, lam) -> torch.Te
     return _EvidentialLossFn.apply(alpha, targets, lam)
 
 
-__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss"]
+class fast_eval_batchnorm:
+    """Context manager: route inference-mode ``F.batch_norm`` on fp32 CUDA tensors to ``train.cu::bn_eval_kernel``.
+
+    Used while the engine runs / captures evaluation forwards (CUDA graphs bake the replacement in).  Training-mode
+    batch norm (batch statistics + running-stat updates) is untouched and stays on cuDNN.
+    """
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._F, self._orig = F, F.batch_norm
+        orig, e = self._orig, ext()
+
+        def batch_norm(input, running_mean, running_var, weight=None, bias=None, training=False, momentum=0.1, eps=1e-5):
+            if (not training and running_mean is not None and input.is_cuda and input.dtype == torch.float32
+                    and not torch.is_grad_enabled()):
+                return e.bn_eval(input, running_mean, running_var, weight, bias, float(eps), False)
+            return orig(input, running_mean, running_var, weight, bias, training, momentum, eps)
+
+        F.batch_norm = batch_norm
+        return self
+
+    def __exit__(self, *exc):
+        self._F.batch_norm = self._orig
+        return False
+
+
+__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss", "fast_eval_batchnorm"]

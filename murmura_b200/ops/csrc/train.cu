@@ -61,6 +61,36 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
     }
 }
 
+// ---- BatchNorm inference (+ optional ReLU) as one per-channel affine pass ---------------------------------------
+// y = (x - mean[c]) * rsqrt(var[c] + eps) * gamma[c] + beta[c].  cuDNN's fp32 inference kernel degenerates on the tiny
+// late-stage feature maps of ResNet-18@32x32 (37 us per call at [B,512,1,1]); this is a plain bandwidth-bound pass.
+// `inner` = elements between consecutive channel indices: 1 for channels_last (NHWC) tensors, H*W for NCHW / [B,C].
+__global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+                                                      const float* __restrict__ var, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, long long n, int C, int inner, int relu) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (inner == 1 && (C & 3) == 0) {                        // NHWC, 4 consecutive channels per thread
+        const long long n4 = n >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const int c = (int)((i << 2) % C);
+            float4 v = reinterpret_cast<const float4*>(x)[i];
+            const float4 m = *reinterpret_cast<const float4*>(mean + c), s2 = *reinterpret_cast<const float4*>(var + c);
+            const float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 b = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x = (v.x - m.x) * rsqrtf(s2.x + eps) * g.x + b.x; v.y = (v.y - m.y) * rsqrtf(s2.y + eps) * g.y + b.y;
+            v.z = (v.z - m.z) * rsqrtf(s2.z + eps) * g.z + b.z; v.w = (v.w - m.w) * rsqrtf(s2.w + eps) * g.w + b.w;
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            reinterpret_cast<float4*>(y)[i] = v;
+        }
+        return;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)((i / inner) % C);
+        float v = (x[i] - mean[c]) * rsqrtf(var[c] + eps) * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
+        y[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+
 // ---- softmax cross-entropy evaluation: one warp per row, device-side accumulators ----------------
 // stats[0] += Σ CE, stats[1] += #correct, stats[2] += #rows  (rows >= n_valid are padding)
 __global__ void ce_eval_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
@@ -215,6 +245,26 @@ void sgd_multi(std::vector<Tensor> params, std::vector<Tensor> grads, double lr)
         mb::sgd_multi_kernel<<<nb, 256, 0, cur_stream()>>>(a, (float)lr);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
     }
+}
+
+Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps, bool relu) {
+    c10::cuda::CUDAGuard guard(x.device());
+    TORCH_CHECK(x.dtype() == torch::kFloat32 && x.dim() >= 2);
+    const int C = (int)x.size(1);
+    int inner;
+    Tensor xin = x;
+    if (x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast) && !(x.size(2) == 1 && x.size(3) == 1)) inner = 1;
+    else if (x.dim() == 4 && x.size(2) == 1 && x.size(3) == 1) { inner = 1; if (!x.is_contiguous() && !x.is_contiguous(at::MemoryFormat::ChannelsLast)) xin = x.contiguous(); }
+    else { if (!x.is_contiguous()) xin = x.contiguous(); inner = 1; for (int d = 2; d < xin.dim(); ++d) inner *= (int)xin.size(d); }
+    Tensor y = torch::empty_like(xin);
+    const long long n = xin.numel();
+    if (n == 0) return y;
+    const int blocks = (int)std::min<long long>(148 * 8, (n / 4 + 255) / 256 + 1);
+    mb::bn_eval_kernel<<<blocks, 256, 0, cur_stream()>>>(xin.data_ptr<float>(), y.data_ptr<float>(), mean.data_ptr<float>(), var.data_ptr<float>(),
+        gamma.has_value() && gamma->defined() ? gamma->data_ptr<float>() : nullptr, beta.has_value() && beta->defined() ? beta->data_ptr<float>() : nullptr,
+        (float)eps, n, C, inner, relu ? 1 : 0);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return y;
 }
 
 void ce_eval(Tensor logits, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats) {

@@ -124,7 +124,7 @@ class ForeignEval:
         self.stage[:n].copy_(src_row[:n], non_blocking=True)
         if self.eng.opt.cuda_graphs:
             if self.graph is None:
-                side = self.eng.capture_streams[self.vn.slot % len(self.eng.capture_streams)]
+                side = self.eng.capture_streams[self.eng.stream_of[self.vn.slot]]
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     self._body()
@@ -237,7 +237,27 @@ class B200Network:
 
         # ---- streams / buffers ---------------------------------------------------------------
         self.main = torch.cuda.current_stream(self.device)
-        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, self.opt.streams))]
+        # Worker streams.  A round's training phase is bounded by its critical path (the node with the most batches: steps of
+        # one node are inherently sequential), so nodes are mapped to streams longest-first and the streams carrying the
+        # longest chains get the highest CUDA priority — their kernels are scheduled ahead of the short chains' kernels.
+        K = max(1, self.opt.streams)
+        lo, hi = -5, 0
+        try:
+            import ctypes
+            _lo, _hi = ctypes.c_int(), ctypes.c_int()
+            if ctypes.CDLL("libcudart.so.12").cudaDeviceGetStreamPriorityRange(ctypes.byref(_lo), ctypes.byref(_hi)) == 0:
+                hi, lo = _lo.value, _hi.value          # API returns (least, greatest); greatest priority is the smallest number
+        except Exception:
+            pass
+        self.streams = [torch.cuda.Stream(self.device, priority=max(lo, min(hi, lo + k))) for k in range(K)]
+        order = sorted(range(len(self.nodes)), key=lambda i: -(self.nodes[i].nb * max(self.nodes[i].eb, 1)))
+        load = [0] * K
+        self.stream_of = [0] * len(self.nodes)
+        for i in order:                                   # LPT: next-longest node → least-loaded stream (ties → higher priority)
+            k = min(range(K), key=lambda j: (load[j], j))
+            self.stream_of[i] = k
+            load[k] += self.nodes[i].nb * max(self.nodes[i].eb, 1) + 1
+        self.launch_order = order
         # One capture stream per worker stream.  cuBLAS keeps one workspace per (handle, stream); graphs captured on
         # the same stream bake in the same workspace pointer, so graphs that may REPLAY concurrently must have been
         # captured on different streams (graphs of one worker stream replay back-to-back and may share).  The
@@ -402,7 +422,7 @@ class B200Network:
         rng = torch.cuda.get_rng_state(self.device)
         vn.model.train()
         vn.perm_buf.copy_(torch.arange(vn.perm_buf.numel(), device=self.device) % vn.n)
-        side = self.capture_streams[vn.slot % len(self.capture_streams)]
+        side = self.capture_streams[self.stream_of[vn.slot]]
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
@@ -433,8 +453,9 @@ class B200Network:
         if isinstance(self.criterion, EvidentialLoss):
             self.lam_t.fill_(self.criterion.anneal(self.round_idx))
         self._fork()
-        for i, vn in enumerate(self.nodes):
-            stream = self.streams[i % len(self.streams)]
+        for i in self.launch_order:
+            vn = self.nodes[i]
+            stream = self.streams[self.stream_of[i]]
             if self._host_shards:                             # per-round H2D of this node's inputs (pinned → HBM)
                 with torch.cuda.stream(stream):
                     vn.X.copy_(self._host_shards[i][0], non_blocking=True)
@@ -672,8 +693,9 @@ class B200Network:
         return state
 
     def _forward_with(self, vn: VirtualNode, state: Optional[Dict[str, torch.Tensor]], xb: torch.Tensor) -> torch.Tensor:
+        from murmura_b200.ops import fast_eval_batchnorm
         vn.model.eval()
-        with torch.no_grad(), self._autocast():
+        with torch.no_grad(), self._autocast(), fast_eval_batchnorm():
             if state is None:
                 return vn.model(xb).float()
             return torch.func.functional_call(vn.model, state, (xb,)).float()
@@ -707,7 +729,7 @@ class B200Network:
         for vi, vn in enumerate(self.nodes):
             if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
                 continue
-            with torch.cuda.stream(self.streams[vi % len(self.streams)]):
+            with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 ev = self._evaluator(vn, vn.eb, "ce")            # CrossEntropyLoss on raw outputs even for evidential models
                 pick = torch.randperm(vn.n, device=self.device)[: vn.eb]
                 ev.load_inputs(vn.X.index_select(0, pick), vn.y.index_select(0, pick))
@@ -739,7 +761,7 @@ class B200Network:
         for vi, vn in enumerate(self.nodes):
             if vn.n == 0:
                 continue
-            with torch.cuda.stream(self.streams[vi % len(self.streams)]):
+            with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
                 take_n = min(vn.n, nbatch * vn.eb)
                 ev = self._evaluator(vn, take_n, "dirichlet")
@@ -873,7 +895,8 @@ class B200Network:
         stats.zero_()
         vn.model.eval()
         EB = max(1, self.opt.eval_batch)
-        with torch.no_grad():
+        from murmura_b200.ops import fast_eval_batchnorm
+        with torch.no_grad(), fast_eval_batchnorm():
             for a in range(0, vn.n, EB):
                 xb, yb = self._inputs(vn, vn.X[a:a + EB]), vn.y[a:a + EB]
                 with self._autocast():
@@ -885,8 +908,9 @@ class B200Network:
 
     def _evaluate(self) -> List[Dict[str, Any]]:
         self._fork()
-        for i, vn in enumerate(self.nodes):
-            stream = self.streams[i % len(self.streams)]
+        for i in self.launch_order:
+            vn = self.nodes[i]
+            stream = self.streams[self.stream_of[i]]
             with torch.cuda.stream(stream):
                 if self.opt.cuda_graphs:
                     if vn.eval_graph is None:
@@ -920,7 +944,7 @@ class B200Network:
         return per_node
 
     def _capture_eval(self, vn: VirtualNode) -> None:
-        side = self.capture_streams[vn.slot % len(self.capture_streams)]
+        side = self.capture_streams[self.stream_of[vn.slot]]
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._eval_node(vn)
@@ -984,7 +1008,7 @@ class B200Network:
         for vi, vn in enumerate(self.nodes):
             if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1:
                 continue
-            with torch.cuda.stream(self.streams[vi % len(self.streams)]):
+            with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 ev = self._evaluator(vn, vn.n, "dirichlet" if self.evidential else "ce")
                 if not getattr(ev, "_full_loaded", False):
                     ev.load_inputs(vn.X, vn.y); ev._full_loaded = not bool(self._host_shards)

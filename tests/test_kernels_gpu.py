@@ -467,3 +467,27 @@ def test_sgd_multi(ext):
     big = torch.zeros(22_000_000, device=DEV); gb = torch.ones_like(big)   # > 320 chunks → split across launches
     ext.sgd_multi([big], [gb], 2.0)
     assert (big == -2.0).all()
+
+
+@pytest.mark.parametrize("shape,cl", [((37, 64, 8, 8), True), ((37, 64, 8, 8), False), ((5, 512, 1, 1), True), ((9, 30, 7, 5), True),
+                                      ((33, 16), False)])
+def test_bn_eval_kernel_and_patch(ext, shape, cl):
+    import torch.nn as nn
+    from murmura_b200.ops import fast_eval_batchnorm
+    g = torch.Generator().manual_seed(len(shape))
+    C = shape[1]
+    x = torch.randn(*shape, generator=g).to(DEV)
+    if cl and len(shape) == 4:
+        x = x.contiguous(memory_format=torch.channels_last)
+    bn = (nn.BatchNorm2d(C) if len(shape) == 4 else nn.BatchNorm1d(C)).to(DEV).eval()
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.randn(C, generator=g)); bn.running_var.copy_(torch.rand(C, generator=g) + 0.3)
+        bn.weight.copy_(torch.randn(C, generator=g)); bn.bias.copy_(torch.randn(C, generator=g))
+        ref = bn(x)
+        with fast_eval_batchnorm():
+            got = bn(x)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(ext.bn_eval(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, 1e-5, True), ref.relu(), rtol=1e-4, atol=1e-5)
+    bn.train()
+    with fast_eval_batchnorm():
+        assert torch.allclose(bn(x), torch.nn.functional.batch_norm(x, None, None, bn.weight, bn.bias, True), atol=1e-4)   # training path untouched
