@@ -1,3 +1,4 @@
 from murmura_b200.cli import app
 
-app()
+if __name__ == "__main__":
+    app()

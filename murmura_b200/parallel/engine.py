@@ -1057,18 +1057,20 @@ class B200Network:
             if verbose:
                 print(f"\n=== Round {r + 1}/{total_rounds} ===")
             prof = self.opt.profile
+            nvtx = torch.cuda.nvtx
             if prof:
-                ev[0].record()
+                ev[0].record(); nvtx.range_push(f"round {r + 1}"); nvtx.range_push("local_training")
             self._local_training(local_epochs, lr)
             if prof:
-                ev[1].record()
+                ev[1].record(); nvtx.range_pop(); nvtx.range_push("exchange+aggregate")
             self._aggregate(parity=r & 1)
             if prof:
-                ev[2].record()
+                ev[2].record(); nvtx.range_pop(); nvtx.range_push("evaluate")
             if (r + 1) % eval_every == 0:
                 per_node = self._evaluate()
                 record_round(self.history, r + 1, per_node, self.compromised if self.attack else None, verbose)
             if prof:
+                nvtx.range_pop(); nvtx.range_pop()
                 ev[3].record(); torch.cuda.synchronize()
                 self.timers["train_ms"] += ev[0].elapsed_time(ev[1]); self.timers["aggregate_ms"] += ev[1].elapsed_time(ev[2])
                 self.timers["eval_ms"] += ev[2].elapsed_time(ev[3])

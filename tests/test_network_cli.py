@@ -213,3 +213,20 @@ def test_experiment_harness(tmp_path):
     again = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "run_suite.py"), str(one), "--results", str(res), "--device", "cpu"],
                            capture_output=True, text=True, env=env, timeout=300)
     assert "1/1 experiments have results" in again.stdout and "ok " not in again.stdout.split("1/1")[0]      # resumed: nothing re-run
+
+
+def test_compat_alias_and_extra_configs():
+    code = ("import murmura_b200.compat as c; c.install_alias(); import murmura; from murmura import Network, Config; "
+            "from murmura.aggregation import KrumAggregator; from murmura.topology import create_topology; "
+            "from murmura.utils import set_seed; print('ALIAS_OK', murmura.__name__)")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert res.returncode == 0 and "ALIAS_OK murmura_b200" in res.stdout, res.stderr[-500:]
+    for name in ("uci_har_dirichlet", "pamap2_dirichlet", "ubar_attack"):
+        cfg = load_config(os.path.join(CFG, name + ".yaml"))
+        cfg.experiment.rounds = 1
+        cfg.data.params["samples_per_node"] = 40
+        if "hidden_dims" not in cfg.model.params:
+            cfg.model.params["hidden_dims"] = [16]
+        torch.manual_seed(0)
+        hist = _build(cfg).train(rounds=1, lr=0.01)
+        assert len(hist["round"]) == 1
