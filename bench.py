@@ -121,7 +121,7 @@ def run_ours(args):
             "data": {"adapter": "synthetic.cifar10", "params": {"samples_per_node": W["samples_per_node"],
                                                                 "partition_method": "dirichlet", "alpha": W["alpha"]}},
             "model": {"factory": "models.resnet18", "params": {"num_classes": 10}},
-            "backend": "b200", "b200": {"stream_inputs": stream_inputs, "streams": 8},
+            "backend": "b200", "b200": {"stream_inputs": stream_inputs, "streams": 8, "transport": args.transport},
         })
         adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
         return Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf), device=device)
@@ -165,7 +165,7 @@ def run_ours(args):
                "config": {"model": "resnet18 (11,191,242 float state elems)", "nodes": W["nodes"], "topology": "fully-connected",
                           "aggregation": "fedavg", "global_batch": W["batch"] * W["nodes"], "samples_per_node": W["samples_per_node"],
                           "batch_size": W["batch"], "local_epochs": W["local_epochs"], "seq_len": None, "lr": W["lr"],
-                          "parallelism": f"{W['nodes']} federated nodes on {world} GPU(s) ({W['nodes'] // world}/GPU), fused P2P exchange+aggregate",
+                          "parallelism": f"{W['nodes']} federated nodes on {world} GPU(s) ({W['nodes'] // world}/GPU), fused exchange+aggregate ({args.transport})",
                           "l2": "flushed between rounds (256 MiB write), one CUDA-event pair per round",
                           "params_per_node": params},
                "clocks": clocks,
@@ -259,6 +259,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--transport", choices=["p2p", "nvls", "nccl"], default="p2p",
+                    help="p2p: in-kernel peer loads (default); nvls: full-mesh FedAvg through multimem.ld_reduce; nccl: baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

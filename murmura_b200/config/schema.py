@@ -110,6 +110,8 @@ class B200Config(BaseModel):
         default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
     channels_last: bool = Field(default=True, description="store 4-D weights / image shards NHWC (tensor-core conv path); "
                                 "aggregation is element-wise so the physical order is irrelevant to it")
+    grouped_mlp: bool = Field(default=True, description="score foreign MLP weights (UBAR stage 2 / EvidentialTrust / DMTT) with the "
+                              "grouped tcgen05 forward (TF32) instead of per-candidate graph replays (fp32)")
     streams: int = Field(default=4, description="concurrent CUDA streams for virtual-node training")
     eval_batch: int = Field(default=1024, description="evaluation micro-batch (results are batch-size independent)")
     flag_timeout_ms: float = Field(default=5000.0, description="device-side wait budget for a peer's publish flag")

@@ -161,6 +161,52 @@ __global__ void __launch_bounds__(kThreads) weighted_gather_kernel(GatherArgs a)
     }
 }
 
+// =============================================================================================
+// NVLS full-mesh FedAvg: out = (1/N)·Σ_{all nodes} θ   with the cross-GPU sum done INSIDE the NVSwitch.
+// The published planes of all ranks are bound to one multicast object; `multimem.ld_reduce.add.v4.f32` on the multicast
+// address returns Σ_ranks of the word at that offset, so each GPU ingests S·P floats instead of (N - V)·P.
+// A Byzantine destination's own term is its live row, not its (attacked) published row: corrected locally.
+// =============================================================================================
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+
+struct NvlsArgs {
+    float* live;                 // [V][stride] local live rows (written)
+    const float* pub_local;      // local published plane for this parity [S][stride]
+    const float* mc_pub;         // multicast address of the same plane
+    size_t stride;
+    int V, S, len4;
+    float inv_n;
+    const uint8_t* byz;          // [V] 1 = destination's own term must be its live row
+    const uint32_t* flags; int G; uint32_t epoch; long long timeout; uint32_t* timed_out;
+};
+
+__global__ void __launch_bounds__(kThreads) nvls_fedavg_kernel(NvlsArgs a) {
+    wait_published(a.flags, a.G, a.epoch, a.timeout, a.timed_out);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.len4; i += gridDim.x * blockDim.x) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < a.S; ++s) {
+            const float4 r = multimem_ld_reduce_add(a.mc_pub + (size_t)s * a.stride + ((size_t)i << 2));
+            sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+        }
+        for (int v = 0; v < a.V; ++v) {
+            float4 o = sum;
+            float4* dst = reinterpret_cast<float4*>(a.live + (size_t)v * a.stride) + i;
+            if (a.byz[v]) {
+                const float4 p = reinterpret_cast<const float4*>(a.pub_local + (size_t)v * a.stride)[i];
+                const float4 l = *dst;
+                o.x += l.x - p.x; o.y += l.y - p.y; o.z += l.z - p.z; o.w += l.w - p.w;
+            }
+            o.x *= a.inv_n; o.y *= a.inv_n; o.z *= a.inv_n; o.w *= a.inv_n;
+            *dst = o;
+        }
+    }
+}
+
 // Stream-ordered wait for all ranks' epoch flags (used before library / TMA kernels that cannot spin themselves).
 __global__ void wait_epoch_kernel(const uint32_t* flags, int G, uint32_t epoch, long long timeout, uint32_t* timed_out) {
     wait_published(flags, G, epoch, timeout, timed_out);
@@ -665,6 +711,22 @@ void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int6
     a.flags = s.flags; a.G = s.G; a.epoch = s.epoch; a.timeout = s.timeout; a.timed_out = s.timed_out;
     dim3 grid(grid_x_for(a.len4, mb::kThreads, (int)V), (unsigned)V);
     mb::weighted_gather_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void nvls_fedavg(Tensor live, int64_t pub_local_ptr, int64_t mc_pub_ptr, int64_t stride, int64_t V, int64_t S, int64_t len,
+                 int64_t N, Tensor byz, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr) {
+    if (V == 0) return;
+    c10::cuda::CUDAGuard guard(live.device());
+    TORCH_CHECK(mc_pub_ptr != 0, "NVLS multicast pointer is null (multicast not supported on this system)");
+    mb::NvlsArgs a;
+    a.live = live.data_ptr<float>(); a.pub_local = reinterpret_cast<const float*>(pub_local_ptr);
+    a.mc_pub = reinterpret_cast<const float*>(mc_pub_ptr); a.stride = (size_t)stride;
+    a.V = (int)V; a.S = (int)S; a.len4 = (int)(len / 4); a.inv_n = 1.f / (float)N; a.byz = byz.data_ptr<uint8_t>();
+    Sync s = make_sync(flags_ptr, G, epoch, timeout_ms, timed_out_ptr);
+    a.flags = s.flags; a.G = s.G; a.epoch = s.epoch; a.timeout = s.timeout; a.timed_out = s.timed_out;
+    const int grid = std::max(1, std::min(148 * 4, (a.len4 + mb::kThreads - 1) / mb::kThreads));
+    mb::nvls_fedavg_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -14,6 +14,8 @@ void publish(Tensor live, int64_t pub_ptr, int64_t stride, int64_t V, int64_t Pf
 void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr,
                      Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, int64_t len, bool renorm,
                      int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
+void nvls_fedavg(Tensor live, int64_t pub_local_ptr, int64_t mc_pub_ptr, int64_t stride, int64_t V, int64_t S, int64_t len,
+                 int64_t N, Tensor byz, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
 void wait_epoch(Tensor anchor, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
 void tail_blend(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
                 Tensor src_slot, Tensor mask, Tensor w_tail, int64_t Pf_pad, Tensor ints, int64_t timed_out_ptr);
@@ -54,6 +56,9 @@ Tensor gram_make_maps(std::vector<int64_t> base_ptrs, int64_t rows, int64_t row_
 int64_t gram_kb_per_stage(int64_t ngroups);
 void gram_tf32(Tensor maps_cpu, std::vector<int64_t> group_map, std::vector<int64_t> group_y, int64_t kb0, int64_t kb1,
                int64_t R, Tensor out, bool zero_out, int64_t max_ctas);
+// mlp_tcgen05.cu
+void grouped_linear_tf32(Tensor groups, int64_t G, int64_t max_m, int64_t K, int64_t N, int64_t ldx, int64_t ldy, int64_t act, double eps);
+void grouped_eval(Tensor groups, int64_t G, int64_t max_m, int64_t C, int64_t ld, bool dirichlet, Tensor stats);
 // dmtt.cu
 void mobility_adjacency(Tensor pos, int64_t round, double area, double range, bool ensure_connected, Tensor adj);
 void liar_claims(Tensor adj, Tensor is_liar, Tensor claims);
@@ -68,6 +73,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("weighted_gather", &weighted_gather);
     m.def("tail_blend", &tail_blend);
     m.def("wait_epoch", &wait_epoch);
+    m.def("nvls_fedavg", &nvls_fedavg);
     m.def("edge_distances", &edge_distances);
     m.def("pairwise_distances", &pairwise_distances);
     m.def("count_sketch", &count_sketch);
@@ -88,6 +94,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("gram_tf32", &gram_tf32);
     m.def("gram_make_maps", &gram_make_maps);
     m.def("gram_kb_per_stage", &gram_kb_per_stage);
+    m.def("grouped_linear_tf32", &grouped_linear_tf32);
+    m.def("grouped_eval", &grouped_eval);
     m.def("mobility_adjacency", &mobility_adjacency);
     m.def("liar_claims", &liar_claims);
     m.def("dmtt_update", &dmtt_update);

@@ -174,7 +174,7 @@ class SymmetricArena:
     CTRL_BYTES = 4096
 
     def __init__(self, layout: StateLayout, placement: Placement, rank: int, device: torch.device,
-                 sketch_size: int = 0, group=None):
+                 sketch_size: int = 0, group=None, backend: str = "ipc"):
         from murmura_b200 import ops
         self.layout, self.placement, self.rank, self.device = layout, placement, rank, device
         self.world = placement.world
@@ -194,53 +194,86 @@ class SymmetricArena:
         self.off_ctrl = _ceil(self.off_sketch_sc + sc_bytes, 4096)
         total = self.off_ctrl + self.CTRL_BYTES
         index = device.index if device.index is not None else torch.cuda.current_device()
-        self._arena = ops.ext().PeerArena(index, total, rank, self.world)
-        if self.world > 1:
+        self.backend = backend if self.world > 1 else "ipc"
+        self.mc_base = 0
+        if self.backend == "symm":
+            # torch symmetric memory: CUDA VMM allocation bound to an NVLS multicast object (multimem.* addresses);
+            # peers are mapped like with cudaIpc, so every kernel works unchanged on this backend.
             import torch.distributed as dist
-            handles: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(handles, self._arena.ipc_handle(), group=group)
-            self._arena.open_peers([bytes(h) for h in handles])
+            import torch.distributed._symmetric_memory as symm_mem
+            self._symm_t = symm_mem.empty(total, dtype=torch.uint8, device=device)
+            self._symm_t.zero_()
+            self._hdl = symm_mem.rendezvous(self._symm_t, (group or dist.group.WORLD))
+            self._bases = [int(p) for p in self._hdl.buffer_ptrs]
+            self.mc_base = int(self._hdl.multicast_ptr or 0)
+            torch.cuda.synchronize(device)
             dist.barrier(group=group)
-        a = self._arena
-        self.live = a.view(rank, self.off_live, [S, stride], torch.float32)
-        self.pub = a.view(rank, self.off_pub, [2, S, stride], torch.float32)
-        self.sketch = a.view(rank, self.off_sketch, [2, S, self.K], torch.float32) if self.K else None
-        self.flags = a.view(rank, self.off_ctrl, [16], torch.int32)
-        self.timed_out = a.view(rank, self.off_ctrl + 64, [1], torch.int32)
+            self._arena = None
+        else:
+            self._arena = ops.ext().PeerArena(index, total, rank, self.world)
+            if self.world > 1:
+                import torch.distributed as dist
+                handles: List[Optional[bytes]] = [None] * self.world
+                dist.all_gather_object(handles, self._arena.ipc_handle(), group=group)
+                self._arena.open_peers([bytes(h) for h in handles])
+                dist.barrier(group=group)
+            self._bases = [self._arena.base_ptr(r) for r in range(self.world)]
+        self.live = self._view(rank, self.off_live, [S, stride], torch.float32)
+        self.pub = self._view(rank, self.off_pub, [2, S, stride], torch.float32)
+        self.sketch = self._view(rank, self.off_sketch, [2, S, self.K], torch.float32) if self.K else None
+        self.flags = self._view(rank, self.off_ctrl, [16], torch.int32)
+        self.timed_out = self._view(rank, self.off_ctrl + 64, [1], torch.int32)
         # device pointer tables (int64[G]) handed to kernels as `const T* const*`
-        self.tbl_pub = a.ptr_table(self.off_pub)
-        self.tbl_live = a.ptr_table(self.off_live)
-        self.tbl_sketch = a.ptr_table(self.off_sketch)
-        self.tbl_sketch_q = a.ptr_table(self.off_sketch_q)
-        self.tbl_sketch_sc = a.ptr_table(self.off_sketch_sc)
-        self.tbl_flags = a.ptr_table(self.off_ctrl)
+        self.tbl_pub = self._ptr_table(self.off_pub)
+        self.tbl_live = self._ptr_table(self.off_live)
+        self.tbl_sketch = self._ptr_table(self.off_sketch)
+        self.tbl_sketch_q = self._ptr_table(self.off_sketch_q)
+        self.tbl_sketch_sc = self._ptr_table(self.off_sketch_sc)
+        self.tbl_flags = self._ptr_table(self.off_ctrl)
+
+    def _view(self, rank: int, byte_offset: int, sizes: List[int], dtype: torch.dtype) -> torch.Tensor:
+        if self._arena is not None:
+            return self._arena.view(rank, byte_offset, sizes, dtype)
+        esize = torch.empty((), dtype=dtype).element_size()
+        if rank == self.rank:
+            n = int(np.prod(sizes)) * esize
+            return self._symm_t[byte_offset:byte_offset + n].view(dtype).view(sizes)
+        return self._hdl.get_buffer(rank, sizes, dtype, byte_offset // esize)
+
+    def _ptr_table(self, byte_offset: int) -> torch.Tensor:
+        return torch.tensor([b + byte_offset for b in self._bases], dtype=torch.int64, device=self.device)
 
     # pointers -----------------------------------------------------------------------------------
     def pub_plane_ptr(self, parity: int) -> int:
-        return self._arena.base_ptr(self.rank) + self.off_pub + parity * self.S * self.layout.stride * 4
+        return self._bases[self.rank] + self.off_pub + parity * self.S * self.layout.stride * 4
+
+    def mc_pub_plane_ptr(self, parity: int) -> int:
+        """Multicast (NVLS) address of the published plane — 0 when the arena has no multicast mapping."""
+        return self.mc_base + self.off_pub + parity * self.S * self.layout.stride * 4 if self.mc_base else 0
 
     def parity_off(self, parity: int) -> int:
         return parity * self.S * self.layout.stride
 
     def base_ptr(self, rank: int) -> int:
-        return self._arena.base_ptr(rank)
+        return self._bases[rank]
 
     def peer_row(self, rank: int, parity: int, slot: int) -> torch.Tensor:
         """Published row of (rank, slot) as a tensor — local or peer-mapped (read in place over NVLink)."""
         off = self.off_pub + ((parity * self.S + slot) * self.layout.stride) * 4
-        return self._arena.view(rank, off, [self.layout.stride], torch.float32)
+        return self._view(rank, off, [self.layout.stride], torch.float32)
 
     def sketch_q_ptr(self) -> int:
-        return self._arena.base_ptr(self.rank) + self.off_sketch_q
+        return self._bases[self.rank] + self.off_sketch_q
 
     def sketch_sc_ptr(self) -> int:
-        return self._arena.base_ptr(self.rank) + self.off_sketch_sc
+        return self._bases[self.rank] + self.off_sketch_sc
 
     def flags_ptr(self) -> int:
-        return self._arena.base_ptr(self.rank) + self.off_ctrl
+        return self._bases[self.rank] + self.off_ctrl
 
     def timed_out_ptr(self) -> int:
-        return self._arena.base_ptr(self.rank) + self.off_ctrl + 64
+        return self._bases[self.rank] + self.off_ctrl + 64
 
     def close(self) -> None:
-        self._arena.close()
+        if self._arena is not None:
+            self._arena.close()

@@ -86,6 +86,58 @@ class VirtualNode:
     graph_key: Any = None
 
 
+def mlp_plan(model: nn.Module, layout: StateLayout) -> Optional[List[Dict[str, Any]]]:
+    """Layer list of the MLP families for the grouped tcgen05 forward; ``None`` for anything else (conv nets …)."""
+    from murmura_b200.models.mlp import MLP, EvidentialMLP
+    ent = {e.name: e for e in layout.entries}
+    plan: List[Dict[str, Any]] = []
+
+    def linear(prefix: str) -> Dict[str, Any]:
+        w = ent[prefix + ".weight"]
+        return {"w": w.offset, "b": ent[prefix + ".bias"].offset if prefix + ".bias" in ent else None, "bn": None, "act": 0,
+                "N": w.shape[0], "K": w.shape[1]}
+
+    if isinstance(model, EvidentialMLP):
+        mods = list(model.feature_extractor.named_children())
+        i = 0
+        while i < len(mods):
+            name, m = mods[i]
+            if not isinstance(m, nn.Linear):
+                return None
+            layer = linear(f"feature_extractor.{name}")
+            j = i + 1
+            while j < len(mods) and not isinstance(mods[j][1], nn.Linear):
+                n2, m2 = mods[j]
+                if isinstance(m2, nn.BatchNorm1d):
+                    pre = f"feature_extractor.{n2}"
+                    layer["bn"] = (ent[pre + ".running_mean"].offset, ent[pre + ".running_var"].offset,
+                                   ent[pre + ".weight"].offset if m2.affine else None, ent[pre + ".bias"].offset if m2.affine else None)
+                    layer["eps"] = m2.eps
+                elif isinstance(m2, nn.ReLU):
+                    layer["act"] = 1
+                elif not isinstance(m2, (nn.Dropout, nn.Identity)):
+                    return None
+                j += 1
+            plan.append(layer)
+            i = j
+        head = linear("evidential_head.fc")
+        head["act"] = 2
+        plan.append(head)
+        return plan
+    if isinstance(model, MLP):
+        mods = list(model.net.named_children())
+        for idx, (name, m) in enumerate(mods):
+            if isinstance(m, nn.Linear):
+                layer = linear(f"net.{name}")
+                if idx + 1 < len(mods) and isinstance(mods[idx + 1][1], nn.ReLU):
+                    layer["act"] = 1
+                plan.append(layer)
+            elif not isinstance(m, nn.ReLU):
+                return None
+        return plan
+    return None
+
+
 class ForeignEval:
     """Score a *foreign* weight row on one node's data (UBAR stage 2, EvidentialTrust, DMTT model scores).
 
@@ -184,7 +236,8 @@ class B200Network:
         probe = model_factory()
         self.layout = StateLayout.from_model(probe, channels_last=bool(self.opt.channels_last))
         sketch_k = int(getattr(self.aggregator, "sketch_size", 0)) if self.family == "sketchguard" else 0
-        self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k)
+        self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k,
+                                    backend="symm" if self.opt.transport == "nvls" else "ipc")
         S, L = self.placement.slots_per_rank, self.layout
         self.S = S
         self.live = self.arena.live
@@ -275,6 +328,8 @@ class B200Network:
         self._lr = None
         self._edge_cache: Dict[Any, Dict[str, torch.Tensor]] = {}
         self._evaluators: Dict[Any, ForeignEval] = {}
+        self._mlp_plan = mlp_plan(self.nodes[0].model, self.layout) if (self.nodes and self.opt.grouped_mlp) else None
+        self._mlp_bufs: Dict[Any, torch.Tensor] = {}
         self._row_cache: Dict[Any, torch.Tensor] = {}
         self._stat_log: List[torch.Tensor] = []
         self._agg_state: Dict[str, torch.Tensor] = {}
@@ -547,6 +602,18 @@ class B200Network:
     def _agg_fedavg(self, et, parity: int) -> None:
         if "fedavg_ready" not in et:
             self.ext.fedavg_weights(*self._et_args(et)); et["fedavg_ready"] = True
+            rows = et["host_rows"]
+            et["full_mesh"] = all(rows[i + 1] - rows[i] == self.N for i in range(len(rows) - 1))
+            et["byz"] = torch.tensor([1 if vn.byzantine else 0 for vn in self.nodes] or [0], dtype=torch.uint8, device=self.device)
+        if (self.opt.transport == "nvls" and self.world > 1 and et["full_mesh"] and self.arena.mc_base
+                and not self.opt.fault_drop_edges):
+            # full mesh ⇒ every node computes the same mean: let the NVSwitch do the cross-GPU sum (multimem.ld_reduce)
+            L = self.layout
+            fp, G, ep, to, tp = self._sync_args()
+            self.ext.nvls_fedavg(self.live, self.arena.pub_plane_ptr(parity), self.arena.mc_pub_plane_ptr(parity), L.stride, self.V,
+                                 self.S, L.Pf_pad, self.N, et["byz"], fp, G, ep, to, tp)
+            self.kernel_launches += 1
+            return                                            # int buffers keep own under FedAvg: nothing to blend
         self._gather(et, parity, renorm=True)
 
     # ---- BALANCE -----------------------------------------------------------------------------
@@ -700,6 +767,68 @@ class B200Network:
                 return vn.model(xb).float()
             return torch.func.functional_call(vn.model, state, (xb,)).float()
 
+    # ---- grouped tcgen05 forward of foreign MLP weights ---------------------------------------------------------
+    def _row_ptr(self, rank: int, parity: Optional[int], slot: int) -> int:
+        """Device address of a published row (``parity`` 0/1) or of a local live row (``parity`` None)."""
+        ar, L = self.arena, self.layout
+        if parity is None:
+            return ar.base_ptr(self.rank) + ar.off_live + slot * L.stride * 4
+        return ar.base_ptr(rank) + ar.off_pub + (parity * self.S + slot) * L.stride * 4
+
+    def _buf(self, key: Any, shape: Tuple[int, ...], dtype=torch.float32) -> torch.Tensor:
+        t = self._mlp_bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self._mlp_bufs[key] = torch.zeros(*shape, dtype=dtype, device=self.device)
+        return t
+
+    def _grouped_mlp_scores(self, jobs: List[Tuple[int, int, int]], inputs: Dict[int, Tuple[torch.Tensor, torch.Tensor]],
+                            kind: str, stats: torch.Tensor) -> None:
+        """``jobs`` = (stats_row, destination vi, weight-row address).  One launch per layer for ALL jobs."""
+        if not jobs:
+            return
+        plan = self._mlp_plan
+        G = len(jobs)
+        max_m = max(inputs[vi][0].shape[0] for _, vi, _ in jobs)
+        host = np.zeros((G, 9), dtype=np.int64)
+        prev = None
+        for li, layer in enumerate(plan):
+            out = self._buf(("act", li, G, max_m), (G, max_m, layer["N"]))
+            for gi, (_, vi, base) in enumerate(jobs):
+                x, _ = inputs[vi]
+                host[gi, 0] = x.data_ptr() if li == 0 else prev[gi].data_ptr()
+                host[gi, 1] = base + layer["w"] * 4
+                host[gi, 2] = base + layer["b"] * 4 if layer["b"] is not None else 0
+                if layer["bn"] is not None:
+                    mean, var, gam, bet = layer["bn"]
+                    host[gi, 3], host[gi, 4] = base + mean * 4, base + var * 4
+                    host[gi, 5] = base + gam * 4 if gam is not None else 0
+                    host[gi, 6] = base + bet * 4 if bet is not None else 0
+                else:
+                    host[gi, 3:7] = 0
+                host[gi, 7] = out[gi].data_ptr()
+                host[gi, 8] = x.shape[0]
+            desc = torch.from_numpy(host.copy()).to(self.device, non_blocking=True)
+            self.ext.grouped_linear_tf32(desc, G, max_m, layer["K"], layer["N"], layer["K"], layer["N"], layer["act"],
+                                         float(layer.get("eps", 1e-5)))
+            prev = out
+        ev = np.zeros((G, 3), dtype=np.int64)
+        for gi, (_, vi, _) in enumerate(jobs):
+            ev[gi] = (prev[gi].data_ptr(), inputs[vi][1].data_ptr(), inputs[vi][0].shape[0])
+        tmp = self._buf(("stats", G), (G, _STAT_COLS))
+        tmp.zero_()
+        self.ext.grouped_eval(torch.from_numpy(ev).to(self.device, non_blocking=True), G, max_m, plan[-1]["N"], plan[-1]["N"],
+                              kind == "dirichlet", tmp)
+        stats.index_copy_(0, torch.tensor([j[0] for j in jobs], device=self.device), tmp)
+        self.kernel_launches += len(plan) + 1
+
+    def _flat_inputs(self, vn: VirtualNode, idx: Optional[torch.Tensor], tag: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        x = vn.X if idx is None else vn.X.index_select(0, idx)
+        y = vn.y if idx is None else vn.y.index_select(0, idx)
+        xb = self._buf((tag, vn.slot, "x"), (x.shape[0], int(np.prod(x.shape[1:]))))
+        yb = self._buf((tag, vn.slot, "y"), (x.shape[0],), dtype=torch.long)
+        xb.copy_(x.reshape(x.shape[0], -1)); yb.copy_(y)
+        return xb, yb
+
     def _evaluator(self, vn: VirtualNode, rows: int, kind: str) -> ForeignEval:
         key = (vn.slot, rows, kind)
         ev = self._evaluators.get(key)
@@ -725,9 +854,18 @@ class B200Network:
         cand_host = cand.cpu()                                       # tiny D2H: which candidates to evaluate
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        if self._mlp_plan is not None:
+            jobs, inputs = [], {}
+            for vi, vn in enumerate(self.nodes):
+                if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
+                    continue
+                inputs[vi] = self._flat_inputs(vn, torch.randperm(vn.n, device=self.device)[: vn.eb], "ubar")
+                jobs.append((rows[vi], vi, self._row_ptr(self.rank, None, vn.slot)))           # own loss from the live row
+                jobs += [(e, vi, self._row_ptr(rk[e], parity, sl[e])) for e in range(rows[vi] + 1, rows[vi + 1]) if cand_host[e] != 0]
+            self._grouped_mlp_scores(jobs, inputs, "ce", stats)
         self._fork()
         for vi, vn in enumerate(self.nodes):
-            if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
+            if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0 or self._mlp_plan is not None:
                 continue
             with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 ev = self._evaluator(vn, vn.eb, "ce")            # CrossEntropyLoss on raw outputs even for evidential models
@@ -757,9 +895,19 @@ class B200Network:
         vac, acc, trust = et["aux"], et["aux2"], et["aux3"]
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        if self._mlp_plan is not None:
+            jobs, inputs = [], {}
+            for vi, vn in enumerate(self.nodes):
+                if vn.n == 0:
+                    continue
+                nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
+                take_n = min(vn.n, nbatch * vn.eb)
+                inputs[vi] = self._flat_inputs(vn, torch.randperm(vn.n, device=self.device)[:take_n], "et")
+                jobs += [(e, vi, self._row_ptr(rk[e], parity, sl[e])) for e in range(rows[vi] + 1, rows[vi + 1])]
+            self._grouped_mlp_scores(jobs, inputs, "dirichlet", stats)
         self._fork()
         for vi, vn in enumerate(self.nodes):
-            if vn.n == 0:
+            if vn.n == 0 or self._mlp_plan is not None:
                 continue
             with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
@@ -1004,9 +1152,17 @@ class B200Network:
         received = torch.zeros(V, N, dtype=torch.uint8, device=self.device)
         rows, rk, sl, gids = et["host_rows"], et["host_rank"], et["host_slot"], et["host_gid"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        if self._mlp_plan is not None:
+            jobs, inputs = [], {}
+            for vi, vn in enumerate(self.nodes):
+                if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1:
+                    continue
+                inputs[vi] = self._flat_inputs(vn, None, "dmtt")
+                jobs += [(e, vi, self._row_ptr(rk[e], parity, sl[e])) for e in range(rows[vi] + 1, rows[vi + 1])]
+            self._grouped_mlp_scores(jobs, inputs, "dirichlet" if self.evidential else "ce", stats)
         self._fork()
         for vi, vn in enumerate(self.nodes):
-            if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1:
+            if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1 or self._mlp_plan is not None:
                 continue
             with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 ev = self._evaluator(vn, vn.n, "dirichlet" if self.evidential else "ce")

@@ -101,7 +101,7 @@ def _assert_states_close(got, want, atol=2e-5):
 ])
 def test_fused_aggregation_matches_cpu_oracle_bn_model(algo, params, attack):
     cfg = _cfg(algo, params, n=6, topo={"type": "k-regular", "num_nodes": 6, "k": 4}, attack=attack, model=HAR, data=HAR_DATA,
-               b200={"krum_gram": "fp32"})
+               b200={"krum_gram": "fp32", "grouped_mlp": False})
     net, adapter, mf = _build(cfg)
     try:
         got, want, own, pub = _oracle_round(net, cfg, adapter, mf)
@@ -116,11 +116,25 @@ def test_fused_aggregation_matches_cpu_oracle_bn_model(algo, params, attack):
 
 def test_fused_evidential_trust_matches_cpu_oracle():
     cfg = _cfg("evidential_trust", {"trust_threshold": 0.05, "self_weight": 0.6, "accuracy_weight": 0.7}, n=5,
-               topo={"type": "fully", "num_nodes": 5}, model=HAR, data=HAR_DATA)
+               topo={"type": "fully", "num_nodes": 5}, model=HAR, data=HAR_DATA, b200={"grouped_mlp": False})
     net, adapter, mf = _build(cfg)
     try:
         got, want, _, _ = _oracle_round(net, cfg, adapter, mf)
         _assert_states_close(got, want, atol=5e-5)
+    finally:
+        net.close()
+
+
+@pytest.mark.parametrize("algo,params", [("evidential_trust", {"trust_threshold": 0.05, "self_weight": 0.6, "accuracy_weight": 0.7}),
+                                         ("ubar", {"rho": 0.6, "alpha": 0.5})])
+def test_grouped_tcgen05_mlp_scoring_path(algo, params):
+    """Same aggregation with the foreign-model scores computed by the grouped tcgen05 (TF32) forward."""
+    cfg = _cfg(algo, params, n=5, topo={"type": "fully", "num_nodes": 5}, model=HAR, data=HAR_DATA, b200={"grouped_mlp": True})
+    net, adapter, mf = _build(cfg)
+    try:
+        assert net._mlp_plan is not None and [l["act"] for l in net._mlp_plan] == [1, 1, 2]
+        got, want, _, _ = _oracle_round(net, cfg, adapter, mf)
+        _assert_states_close(got, want, atol=3e-3)            # trust weights carry TF32 (10-bit mantissa) forward error
     finally:
         net.close()
 

@@ -491,3 +491,48 @@ def test_bn_eval_kernel_and_patch(ext, shape, cl):
     bn.train()
     with fast_eval_batchnorm():
         assert torch.allclose(bn(x), torch.nn.functional.batch_norm(x, None, None, bn.weight, bn.bias, True), atol=1e-4)   # training path untouched
+
+
+@pytest.mark.parametrize("K,N,act,bn", [(561, 256, 1, True), (256, 128, 1, True), (128, 6, 2, False), (4000, 512, 1, True), (784, 200, 1, False),
+                                        (200, 10, 0, False)])
+def test_grouped_linear_tcgen05(ext, K, N, act, bn):
+    """Grouped tf32 linear + fused bias/BN/activation epilogue vs fp64 torch, ragged M per group, unaligned rows (K=561)."""
+    g = torch.Generator().manual_seed(K + N)
+    Ms = [100, 128, 37, 200]
+    G = len(Ms)
+    maxm = max(Ms)
+    X = [torch.randn(m, K, generator=g).to(DEV) for m in Ms]
+    blob = torch.randn(G, N * K + 5 * N + 3, generator=g).to(DEV)          # weights at odd offsets like an arena row
+    Y = torch.zeros(G, maxm, N, device=DEV)
+    host = np.zeros((G, 9), dtype=np.int64)
+    refs = []
+    for i in range(G):
+        off = 1 + i                                                        # deliberately misaligned
+        W = blob[i, off:off + N * K].view(N, K); b = blob[i, off + N * K: off + N * K + N]
+        mean = blob[i, off + N * K + N: off + N * K + 2 * N]; var = blob[i, off + N * K + 2 * N: off + N * K + 3 * N].abs() + 0.5
+        blob[i, off + N * K + 2 * N: off + N * K + 3 * N] = var
+        gam = blob[i, off + N * K + 3 * N: off + N * K + 4 * N]; bet = blob[i, off + N * K + 4 * N: off + N * K + 5 * N]
+        host[i] = (X[i].data_ptr(), W.data_ptr(), b.data_ptr(), mean.data_ptr() if bn else 0, var.data_ptr() if bn else 0,
+                   gam.data_ptr() if bn else 0, bet.data_ptr() if bn else 0, Y[i].data_ptr(), Ms[i])
+        z = X[i].double() @ W.double().T + b.double()
+        if bn:
+            z = (z - mean.double()) / torch.sqrt(var.double() + 1e-5) * gam.double() + bet.double()
+        z = z.relu() if act == 1 else (torch.nn.functional.softplus(z) + 1 if act == 2 else z)
+        refs.append(z.float())
+    ext.grouped_linear_tf32(torch.from_numpy(host).to(DEV), G, maxm, K, N, K, N, act, 1e-5)
+    torch.cuda.synchronize()
+    for i in range(G):
+        got = Y[i, :Ms[i]]
+        scale = refs[i].abs().max().item() + 1e-6
+        assert ((got - refs[i]).abs().max().item() / scale) < 4e-3, (i, (got - refs[i]).abs().max().item(), scale)
+        assert (Y[i, Ms[i]:] == 0).all()                                    # rows past M are never written
+    # grouped metrics on the outputs
+    if act == 2 or act == 0:
+        C = N
+        tg = [torch.randint(0, C, (m,), generator=g).to(DEV) for m in Ms]
+        ev = np.array([[Y[i].data_ptr(), tg[i].data_ptr(), Ms[i]] for i in range(G)], dtype=np.int64)
+        stats = torch.zeros(G, 8, device=DEV)
+        ext.grouped_eval(torch.from_numpy(ev).to(DEV), G, maxm, C, N, act == 2, stats)
+        for i in range(G):
+            ref = R.dirichlet_stats(Y[i, :Ms[i]].cpu(), tg[i].cpu()) if act == 2 else R.ce_stats(Y[i, :Ms[i]].cpu(), tg[i].cpu())
+            assert torch.allclose(stats[i, :len(ref)].cpu(), ref.float(), rtol=3e-4, atol=1e-3)
