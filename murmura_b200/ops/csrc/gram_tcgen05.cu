@@ -100,6 +100,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// Thread-block clusters: the `csize` CTAs of a cluster own adjacent K-slices and merge their partial R×R tiles through
+// distributed shared memory (red.shared::cluster into the leader CTA's smem) before ONE CTA per cluster touches global
+// memory — csize× fewer global fp32 reductions on the R×R result.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_red_add(uint32_t local_smem_addr, uint32_t target_cta, float v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(target_cta));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.f32 [%0], %1;" :: "r"(remote), "f"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramGroups grp, int kb0, int kb1, int n_mma, int R,
                  float* __restrict__ out /*[128][128]*/) {
@@ -177,27 +191,50 @@ gram_tf32_kernel(const __grid_constant__ GramMaps maps, const GramGroups grp, in
                 }
                 umma_commit(&accum_bar);                                     // accumulator complete
             }
-        } else {
-            // ===== epilogue: TMEM → registers → fp32 reductions into the global R×R tile =====
-            mbar_wait_backoff(&accum_bar, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-            const int row = q * 32 + lane;
-            for (int c0 = 0; c0 < n_mma; c0 += 16) {
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                             : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < R) {
+        }
+    }
+    // ===== epilogue: TMEM → registers → (cluster DSMEM reduce) → fp32 reductions into the global R×R tile =====
+    // The pipeline stages are dead once every CTA of the cluster finished its main loop, so the leader's first stage
+    // is reused as the R×R (<= 64 KiB) reduction buffer.
+    const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+    float* red = reinterpret_cast<float*>(smem);
+    if (num_steps > 0) {                                                 // this CTA's MMAs have retired → its smem stages are dead
+        mbar_wait_backoff(&accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (csize > 1) {
+        cluster_sync_all();                                              // every CTA of the cluster is past its main loop
+        if (crank == 0)
+            for (int i = threadIdx.x; i < R * R; i += blockDim.x) red[i] = 0.f;
+        cluster_sync_all();
+    }
+    if (warp >= 2) {
+        const int q = warp & 3;                                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        for (int c0 = 0; c0 < n_mma && num_steps > 0; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < R) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < R) atomicAdd(out + row * kGramRows + c0 + j, __uint_as_float(r[j]));
+                for (int j = 0; j < 16; ++j) {
+                    if (c0 + j >= R) break;
+                    const float v = __uint_as_float(r[j]);
+                    if (csize > 1) dsmem_red_add(smem_u32(red + row * R + c0 + j), 0u, v);
+                    else atomicAdd(out + row * kGramRows + c0 + j, v);
                 }
             }
         }
+    }
+    if (csize > 1) {
+        cluster_sync_all();                                              // every CTA's partial tile has landed in the leader
+        if (crank == 0)
+            for (int i = threadIdx.x; i < R * R; i += blockDim.x)
+                atomicAdd(out + (i / R) * kGramRows + (i % R), red[i]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -305,7 +342,28 @@ void gram_tf32(Tensor maps_cpu, std::vector<int64_t> group_map, std::vector<int6
     int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
     if (max_ctas > 0) sms = std::min<int>(sms, (int)max_ctas);
     const int64_t steps = (kb1 - kb0 + grp.kb_per_stage - 1) / grp.kb_per_stage;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (steps + 3) / 4));      // >= 4 super-steps per CTA
-    mb::gram_tf32_kernel<<<grid, mb::kGramThreads, smem, stream>>>(maps, grp, (int)kb0, (int)kb1, n_mma, (int)R, out.data_ptr<float>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (steps + 3) / 4));      // >= 4 super-steps per CTA
+    // Cluster of 2 CTAs (a TPC pair: 148 = 2·74 packs every SM; clusters of 4 strand SMs on 16/18/20-SM GPCs and cost a
+    // second wave at one CTA per SM).  The grid is clamped to the number of clusters that can be co-resident.
+    int csize = (grid >= 2 && R * R * 4 <= smem - 1024) ? 2 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(mb::kGramThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (csize > 1) {
+        cfg.gridDim = dim3(grid / csize * csize);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, mb::gram_tf32_kernel, &cfg) == cudaSuccess && max_clusters > 0)
+            grid = std::min(grid, max_clusters * csize);
+        else
+            (void)cudaGetLastError();
+    }
+    grid = std::max(csize, grid / csize * csize);
+    cfg.gridDim = dim3(grid);
+    float* outp = out.data_ptr<float>();
+    int kb0i = (int)kb0, kb1i = (int)kb1, Ri = (int)R;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, mb::gram_tf32_kernel, maps, grp, kb0i, kb1i, n_mma, Ri, outp);
+    TORCH_CHECK(err == cudaSuccess, "gram_tf32 launch failed: ", cudaGetErrorString(err));
 }

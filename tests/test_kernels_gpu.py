@@ -502,15 +502,16 @@ def test_grouped_linear_tcgen05(ext, K, N, act, bn):
     G = len(Ms)
     maxm = max(Ms)
     X = [torch.randn(m, K, generator=g).to(DEV) for m in Ms]
-    blob = torch.randn(G, N * K + 5 * N + 3, generator=g).to(DEV)          # weights at odd offsets like an arena row
+    blob = torch.randn(G, N * K + 5 * N + 16, generator=g).to(DEV)          # weights at odd offsets like an arena row
     Y = torch.zeros(G, maxm, N, device=DEV)
     host = np.zeros((G, 9), dtype=np.int64)
     refs = []
     for i in range(G):
         off = 1 + i                                                        # deliberately misaligned
         W = blob[i, off:off + N * K].view(N, K); b = blob[i, off + N * K: off + N * K + N]
-        mean = blob[i, off + N * K + N: off + N * K + 2 * N]; var = blob[i, off + N * K + 2 * N: off + N * K + 3 * N].abs() + 0.5
-        blob[i, off + N * K + 2 * N: off + N * K + 3 * N] = var
+        mean = blob[i, off + N * K + N: off + N * K + 2 * N]
+        var = blob[i, off + N * K + 2 * N: off + N * K + 3 * N]
+        var.copy_(var.abs() + 0.5)                                         # in place: the kernel reads this very memory
         gam = blob[i, off + N * K + 3 * N: off + N * K + 4 * N]; bet = blob[i, off + N * K + 4 * N: off + N * K + 5 * N]
         host[i] = (X[i].data_ptr(), W.data_ptr(), b.data_ptr(), mean.data_ptr() if bn else 0, var.data_ptr() if bn else 0,
                    gam.data_ptr() if bn else 0, bet.data_ptr() if bn else 0, Y[i].data_ptr(), Ms[i])
