@@ -82,6 +82,7 @@ class VirtualNode:
     arange: Optional[torch.Tensor] = None
     loss_sum: Optional[torch.Tensor] = None
     train_graph: Any = None
+    steps_per_replay: int = 1
     eval_graph: Any = None
     graph_key: Any = None
 
@@ -486,8 +487,10 @@ class B200Network:
         torch.cuda.current_stream().wait_stream(side)
         vn.step.zero_()
         graph = torch.cuda.CUDAGraph()
+        vn.steps_per_replay = (vn.perm_buf.numel() // vn.eb) if self.opt.unroll_round else 1
         with torch.cuda.graph(graph, stream=side):
-            self._train_step(vn, lr)
+            for _ in range(vn.steps_per_replay):          # the device-side step counter walks the permutation buffer
+                self._train_step(vn, lr)
         vn.train_graph = graph
         self.live[vn.slot].copy_(snap); self.ints[vn.slot].copy_(snap_i)
         vn.step.zero_(); vn.loss_sum.zero_()
@@ -523,10 +526,11 @@ class B200Network:
                 vn.perm_buf.copy_(keys.argsort(dim=1)[:, :take].reshape(-1))
                 vn.step.zero_(); vn.loss_sum.zero_()
                 vn.model.train()
-                for _ in range(epochs * vn.nb):
-                    if vn.train_graph is not None:
+                if vn.train_graph is not None:
+                    for _ in range(epochs * vn.nb // vn.steps_per_replay):
                         vn.train_graph.replay()
-                    else:
+                else:
+                    for _ in range(epochs * vn.nb):
                         self._train_step(vn, lr)
                 self.kernel_launches += epochs * vn.nb * (2 if self._fused_evidential else 1)
         self._join()

@@ -230,3 +230,16 @@ def test_compat_alias_and_extra_configs():
         torch.manual_seed(0)
         hist = _build(cfg).train(rounds=1, lr=0.01)
         assert len(hist["round"]) == 1
+
+
+def test_generate_figures(tmp_path):
+    import json
+    res = {"uci_har__fedavg__none0__ring__a0.5": {"status": "ok", "final_accuracy": 0.9, "final_std": 0.01, "convergence_round": 3,
+                                                   "rounds": [{"round": 1, "mean_accuracy": 0.5, "std_accuracy": 0.1}, {"round": 2, "mean_accuracy": 0.9, "std_accuracy": 0.01}]},
+           "bad": {"status": "failed", "rounds": []}}
+    (tmp_path / "r.json").write_text(json.dumps(res))
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "generate_figures.py"), str(tmp_path / "r.json"), "--out", str(tmp_path / "fig")],
+                         capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert run.returncode == 0, run.stderr
+    md = (tmp_path / "fig" / "summary.md").read_text()
+    assert "uci_har__fedavg__none0__ring__a0.5" in md and "0.9000" in md and "bad" not in md
