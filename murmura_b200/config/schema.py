@@ -110,11 +110,13 @@ class B200Config(BaseModel):
         default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
     channels_last: bool = Field(default=True, description="store 4-D weights / image shards NHWC (tensor-core conv path); "
                                 "aggregation is element-wise so the physical order is irrelevant to it")
+    placement: Literal["balanced", "contiguous"] = Field(
+        default="balanced", description="virtual-node → GPU map: balanced = longest-shard-first onto the least-loaded GPU")
     unroll_round: bool = Field(default=True, description="capture ALL local steps of a node's round (epochs x batches) in one CUDA "
                                "graph instead of one graph per step (fewer graph launches; matters for tiny models)")
     grouped_mlp: bool = Field(default=True, description="score foreign MLP weights (UBAR stage 2 / EvidentialTrust / DMTT) with the "
                               "grouped tcgen05 forward (TF32) instead of per-candidate graph replays (fp32)")
-    streams: int = Field(default=4, description="concurrent CUDA streams for virtual-node training")
+    streams: int = Field(default=0, description="concurrent CUDA streams for virtual-node training (0 = auto: min(16, nodes on this GPU))")
     eval_batch: int = Field(default=1024, description="evaluation micro-batch (results are batch-size independent)")
     flag_timeout_ms: float = Field(default=5000.0, description="device-side wait budget for a peer's publish flag")
     fault_drop_edges: Dict[int, list] = Field(

@@ -64,7 +64,7 @@ void mobility_adjacency(Tensor pos, int64_t round, double area, double range, bo
 void liar_claims(Tensor adj, Tensor is_liar, Tensor claims);
 void dmtt_update(Tensor adj, Tensor claims, Tensor collab, Tensor received, Tensor model_score, Tensor score_valid, Tensor c_hat,
                  Tensor alpha, Tensor beta, Tensor next_collab, Tensor q_out, double rho, double lam, double w_d, double w_x,
-                 double tau_U, double eta, double l1, double l2, double l3, int64_t B, int64_t node0);
+                 double tau_U, double eta, double l1, double l2, double l3, int64_t B, Tensor gids);
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "murmura_b200 sm_100a kernels";

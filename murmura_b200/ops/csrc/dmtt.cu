@@ -47,7 +47,8 @@ __global__ void liar_claims_kernel(const uint8_t* __restrict__ adj, const uint8_
     claims[p] = (adj[p] || (i != j && is_liar[i] && is_liar[j])) ? 1 : 0;
 }
 
-// One warp per local node i (global id node0 + blockIdx.x).
+// One block per local node i (global id gids[blockIdx.x]).
+//   gids    [V]     global ids of the local nodes (any placement)
 //   collab  [N][N]  C^{t-1}: row i = peers i sent to / expected from (all ranks' rows, gathered)
 //   received[V][N]  states/claims that actually arrived at i this round
 //   claims  [N][N]  claimed neighbourhoods; adj [N][N] ground-truth G^t
@@ -57,11 +58,11 @@ __global__ void dmtt_update_kernel(const uint8_t* __restrict__ adj, const uint8_
                                    const uint8_t* __restrict__ collab, const uint8_t* __restrict__ received,
                                    const float* __restrict__ model_score, const uint8_t* __restrict__ score_valid,
                                    float* __restrict__ c_hat, float* __restrict__ alpha, float* __restrict__ beta,
-                                   uint8_t* __restrict__ next_collab, float* __restrict__ q_out, int N, int node0,
+                                   uint8_t* __restrict__ next_collab, float* __restrict__ q_out, int N, const int* __restrict__ gids,
                                    float rho, float lam, float w_d, float w_x, float tau_U, float eta,
                                    float l1, float l2, float l3, int B) {
     extern __shared__ float s_q[];                  // [N]
-    const int vi = blockIdx.x, i = node0 + vi;
+    const int vi = blockIdx.x, i = gids[vi];
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         const size_t ij = (size_t)vi * N + j;
         float c = c_hat[ij], a = alpha[ij], b = beta[ij];
@@ -116,14 +117,14 @@ void liar_claims(Tensor adj, Tensor is_liar, Tensor claims) {
 
 void dmtt_update(Tensor adj, Tensor claims, Tensor collab, Tensor received, Tensor model_score, Tensor score_valid, Tensor c_hat,
                  Tensor alpha, Tensor beta, Tensor next_collab, Tensor q_out, double rho, double lam, double w_d, double w_x,
-                 double tau_U, double eta, double l1, double l2, double l3, int64_t B, int64_t node0) {
+                 double tau_U, double eta, double l1, double l2, double l3, int64_t B, Tensor gids) {
     c10::cuda::CUDAGuard guard(adj.device());
     const int N = (int)adj.size(0), V = (int)c_hat.size(0);
     if (V == 0) return;
     mb::dmtt_update_kernel<<<V, 64, N * sizeof(float), cur_stream()>>>(
         adj.data_ptr<uint8_t>(), claims.data_ptr<uint8_t>(), collab.data_ptr<uint8_t>(), received.data_ptr<uint8_t>(),
         model_score.data_ptr<float>(), score_valid.data_ptr<uint8_t>(), c_hat.data_ptr<float>(), alpha.data_ptr<float>(),
-        beta.data_ptr<float>(), next_collab.data_ptr<uint8_t>(), q_out.data_ptr<float>(), N, (int)node0, (float)rho, (float)lam,
+        beta.data_ptr<float>(), next_collab.data_ptr<uint8_t>(), q_out.data_ptr<float>(), N, gids.data_ptr<int>(), (float)rho, (float)lam,
         (float)w_d, (float)w_x, (float)tau_U, (float)eta, (float)l1, (float)l2, (float)l3, (int)B);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

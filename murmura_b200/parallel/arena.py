@@ -146,26 +146,43 @@ class StateLayout:
                     mod._buffers[leaf] = view
 
 
-@dataclass
 class Placement:
-    """Contiguous packing of N nodes onto G ranks (first ``N % G`` ranks host one extra node)."""
-    num_nodes: int
-    world: int
+    """Node → (rank, slot) map.
 
-    def __post_init__(self) -> None:
-        base, rem = divmod(self.num_nodes, self.world)
-        self.counts = [base + (1 if r < rem else 0) for r in range(self.world)]
-        self.starts = np.concatenate([[0], np.cumsum(self.counts)]).tolist()
+    ``weights=None``: contiguous packing (first ``N % G`` ranks host one extra node).  With per-node work weights
+    (local SGD steps per round) nodes are assigned longest-first to the least-loaded rank (LPT) under the same
+    per-rank capacity, so the per-round critical path ``max_rank Σ work`` is balanced — a round ends when the slowest GPU
+    has finished training its virtual nodes.
+    """
+
+    def __init__(self, num_nodes: int, world: int, weights: Optional[List[float]] = None):
+        self.num_nodes, self.world = num_nodes, world
+        base, rem = divmod(num_nodes, world)
+        self.counts = [base + (1 if r < rem else 0) for r in range(world)]
         self.slots_per_rank = max(self.counts) if self.counts else 0
-        self.rank_of = np.zeros(self.num_nodes, dtype=np.int32)
-        self.slot_of = np.zeros(self.num_nodes, dtype=np.int32)
-        for r in range(self.world):
-            for s in range(self.counts[r]):
-                self.rank_of[self.starts[r] + s] = r
-                self.slot_of[self.starts[r] + s] = s
+        self.rank_of = np.zeros(num_nodes, dtype=np.int32)
+        self.slot_of = np.zeros(num_nodes, dtype=np.int32)
+        self._members: List[List[int]] = [[] for _ in range(world)]
+        if weights is None:
+            g = 0
+            for r in range(world):
+                for _ in range(self.counts[r]):
+                    self._members[r].append(g); g += 1
+        else:
+            cap = list(self.counts)
+            load = [0.0] * world
+            for g in sorted(range(num_nodes), key=lambda i: (-float(weights[i]), i)):
+                r = min((r for r in range(world) if len(self._members[r]) < cap[r]), key=lambda r: (load[r], r))
+                self._members[r].append(g); load[r] += float(weights[g])
+            for r in range(world):
+                self._members[r].sort()
+        for r in range(world):
+            for s, g in enumerate(self._members[r]):
+                self.rank_of[g] = r; self.slot_of[g] = s
+        self.starts = np.concatenate([[0], np.cumsum(self.counts)]).tolist()
 
     def local_nodes(self, rank: int) -> List[int]:
-        return list(range(self.starts[rank], self.starts[rank + 1]))
+        return list(self._members[rank])
 
 
 class SymmetricArena:

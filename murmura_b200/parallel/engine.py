@@ -233,7 +233,12 @@ class B200Network:
         self.family = getattr(self.aggregator, "kernel_family", "generic")
 
         # ---- arena ---------------------------------------------------------------------------
-        self.placement = Placement(self.N, self.world)
+        weights = None
+        if self.opt.placement == "balanced" and self.world > 1:
+            bs_ = config.training.batch_size
+            sizes = [len(p) for p in dataset_adapter.get_client_partitions()]
+            weights = [0.0 if i in self.compromised else float(max(1, n // max(1, min(bs_, max(2, n))))) for i, n in enumerate(sizes[: self.N])]
+        self.placement = Placement(self.N, self.world, weights)
         probe = model_factory()
         self.layout = StateLayout.from_model(probe, channels_last=bool(self.opt.channels_last))
         sketch_k = int(getattr(self.aggregator, "sketch_size", 0)) if self.family == "sketchguard" else 0
@@ -294,7 +299,7 @@ class B200Network:
         # Worker streams.  A round's training phase is bounded by its critical path (the node with the most batches: steps of
         # one node are inherently sequential), so nodes are mapped to streams longest-first and the streams carrying the
         # longest chains get the highest CUDA priority — their kernels are scheduled ahead of the short chains' kernels.
-        K = max(1, self.opt.streams)
+        K = max(1, self.opt.streams) if self.opt.streams > 0 else max(1, min(16, len(self.nodes)))
         lo, hi = -5, 0
         try:
             import ctypes
@@ -1186,10 +1191,9 @@ class B200Network:
             vi_t = torch.tensor(ev_i, device=self.device); e_t = torch.tensor(ee_i, device=self.device)
             g_t = et["src_gid"].long().index_select(0, e_t)
             score[vi_t, g_t] = s_e.index_select(0, e_t); valid[vi_t, g_t] = 1; received[vi_t, g_t] = 1
-        node0 = self.local_gids[0] if self.local_gids else 0
         self.ext.dmtt_update(self.adj_dev, self.claims_dev, self.collab, received, score, valid, self.c_hat, self.t_alpha,
                              self.t_beta, self.next_collab, self.q_out, d.rho, d.lambda_forget, d.w_d, d.w_x, d.tau_U, d.eta,
-                             d.lambda1, d.lambda2, d.lambda3, int(d.budget_B), int(node0))
+                             d.lambda1, d.lambda2, d.lambda3, int(d.budget_B), self.node_gid)
         self.kernel_launches += 1
         S = self.placement.slots_per_rank
         local = torch.zeros(S, N, dtype=torch.uint8, device=self.device)

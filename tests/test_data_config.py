@@ -167,3 +167,10 @@ def test_state_layout_and_channels_last_permutation():
     p = Placement(20, 8)
     assert p.counts == [3, 3, 3, 3, 2, 2, 2, 2] and p.slots_per_rank == 3 and p.local_nodes(4) == [12, 13]
     assert int(p.rank_of[13]) == 4 and int(p.slot_of[13]) == 1 and Placement(4, 8).counts == [1, 1, 1, 1, 0, 0, 0, 0]
+    w = [11, 12, 7, 8, 9, 7, 3, 3]                         # steps per node of the flagship shards
+    b = Placement(8, 2, w)
+    loads = [sum(w[g] for g in b.local_nodes(r)) for r in range(2)]
+    assert sorted(loads) == [30, 30] and sorted(b.local_nodes(0) + b.local_nodes(1)) == list(range(8))
+    assert all(int(b.slot_of[g]) == b.local_nodes(int(b.rank_of[g])).index(g) for g in range(8))
+    c = Placement(8, 2)
+    assert [sum(w[g] for g in c.local_nodes(r)) for r in range(2)] == [38, 22]

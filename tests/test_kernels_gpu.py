@@ -393,7 +393,8 @@ def test_mobility_and_dmtt_kernels(ext):
     claims_np = claims.cpu().numpy().astype(bool)
     for rnd in range(2):
         ext.dmtt_update(adj, claims, collab.to(DEV), received.to(DEV), score.to(DEV), valid.to(DEV), c_hat, al, be, nxt, q, cfg.rho,
-                        cfg.lambda_forget, cfg.w_d, cfg.w_x, cfg.tau_U, cfg.eta, cfg.lambda1, cfg.lambda2, cfg.lambda3, cfg.budget_B, node0)
+                        cfg.lambda_forget, cfg.w_d, cfg.w_x, cfg.tau_U, cfg.eta, cfg.lambda1, cfg.lambda2, cfg.lambda3, cfg.budget_B,
+                        torch.arange(node0, node0 + V, dtype=torch.int32, device=DEV))
         for v in range(V):
             i = node0 + v
             st = states[v]
