@@ -853,14 +853,29 @@ class B200Network:
         return row
 
     # ---- UBAR --------------------------------------------------------------------------------
-    def _agg_ubar(self, et, parity: int) -> None:
+    def _ubar_prepare(self, et, parity: int) -> None:
+        """Stage 1 (distances → shortlist) + an ASYNC copy of the shortlist to pinned memory; the host only waits for it
+        in ``_agg_ubar``, after it has enqueued whatever else the round needs (e.g. the DMTT scoring)."""
         a = self.aggregator
         self._edge_dist(et, parity, self.layout.stride)
+        self.ext.ubar_stage1(*self._et_args(et), et["d2"], a.rho, a.min_neighbors, et["aux"], et["aux2"], self._sync_args()[4])
+        self.kernel_launches += 1
+        E = et["aux"].numel()
+        if getattr(self, "_cand_pinned", None) is None or self._cand_pinned.numel() < E:
+            self._cand_pinned = torch.zeros(max(E, 1024)).pin_memory()
+            self._cand_event = torch.cuda.Event()
+        self._cand_pinned[:E].copy_(et["aux"], non_blocking=True)
+        self._cand_event.record()
+        et["ubar_prepared"] = self.epoch
+
+    def _agg_ubar(self, et, parity: int) -> None:
+        a = self.aggregator
+        if et.get("ubar_prepared") != self.epoch:
+            self._ubar_prepare(et, parity)
         tp = self._sync_args()[4]
         cand, rank_t, loss, own_loss = et["aux"], et["aux2"], et["aux3"], et["n2"]
-        self.ext.ubar_stage1(*self._et_args(et), et["d2"], a.rho, a.min_neighbors, cand, rank_t, tp)
-        self.kernel_launches += 1
-        cand_host = cand.cpu()                                       # tiny D2H: which candidates to evaluate
+        self._cand_event.synchronize()                               # tiny D2H issued earlier: which candidates to evaluate
+        cand_host = self._cand_pinned[: cand.numel()]
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
         if self._mlp_plan is not None:
@@ -1038,6 +1053,8 @@ class B200Network:
         if self.world > 1:
             self.arena.timed_out.zero_()
         self._publish(parity)
+        if self.family == "ubar":
+            self._ubar_prepare(et, parity)
         if self.dmtt_on:
             self._dmtt_score_and_update(et, parity)
         plan = getattr(self, f"_agg_{self.family}", self._agg_generic)
@@ -1148,7 +1165,9 @@ class B200Network:
         self.ext.liar_claims(adj, self.is_liar, self.claims_dev)
         if self.collab is None:                              # round 0: C_i = G^0 neighbours
             self.collab = adj.clone()
-        c = self.collab.cpu().numpy().astype(bool)           # N×N bytes D2H: next round's directed edge list
+            self._stage_collab()
+        self._collab_event.synchronize()                     # N×N bytes, copied asynchronously when C^t was produced
+        c = self._collab_pinned.numpy().astype(bool).copy()  # next round's directed edge list
         self._received = c & c.T                             # j's state reaches i iff i∈C_j and j∈C_i (i only accepts expected senders)
         return [np.flatnonzero(self._received[i]).tolist() for i in range(self.N)]
 
@@ -1206,6 +1225,14 @@ class B200Network:
         rows_idx = torch.tensor([int(self.placement.rank_of[g]) * S + int(self.placement.slot_of[g]) for g in range(N)],
                                 device=self.device)
         self.collab = full.index_select(0, rows_idx).contiguous()
+        self._stage_collab()
+
+    def _stage_collab(self) -> None:
+        if getattr(self, "_collab_pinned", None) is None:
+            self._collab_pinned = torch.zeros(self.N, self.N, dtype=torch.uint8).pin_memory()
+            self._collab_event = torch.cuda.Event()
+        self._collab_pinned.copy_(self.collab, non_blocking=True)
+        self._collab_event.record()
 
     # =========================================================================================
     # round loop
@@ -1304,6 +1331,8 @@ class B200Network:
             d = blob["dmtt"]
             self.c_hat.copy_(d["c_hat"]); self.t_alpha.copy_(d["alpha"]); self.t_beta.copy_(d["beta"])
             self.collab = None if d["collab"] is None else d["collab"].to(self.device)
+            if self.collab is not None:
+                self._stage_collab()
         if self.family == "sketchguard" and "sk_hist" in blob:
             self.sk_hist.copy_(blob["sk_hist"])
         if self.world > 1:      # epochs must stay monotone across the job; re-align on the max
