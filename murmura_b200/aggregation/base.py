@@ -10,7 +10,7 @@ helpers share the same semantics and are cross-checked in ``tests/``.
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, Optional, Sequence
 
 import torch
 

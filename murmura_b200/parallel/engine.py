@@ -22,9 +22,10 @@ NCCL is only used for bootstrap (IPC-handle exchange) and for tiny control tenso
 """
 from __future__ import annotations
 
+import contextlib
+import io
 import math
 import os
-import time
 from contextlib import nullcontext
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Tuple
@@ -225,7 +226,6 @@ class B200Network:
         t = config.topology
         self.mobility = build_mobility_model(config)
         self.topology: Topology = create_topology(t.type, t.num_nodes, p=t.p, k=t.k, seed=t.seed)
-        import contextlib, io
         with (contextlib.redirect_stdout(io.StringIO()) if not self.is_primary else nullcontext()):
             self.attack = build_attack(config)
         self.compromised = set(self.attack.get_compromised_nodes()) if self.attack else set()
@@ -761,13 +761,6 @@ class B200Network:
         self.kernel_launches += 1
 
     # ---- forward evaluation of foreign weights (UBAR stage 2, EvidentialTrust, DMTT scoring) ----------------
-    def _foreign_state(self, rank: int, parity: int, slot: int, vn: VirtualNode) -> Dict[str, torch.Tensor]:
-        row = self.arena.peer_row(rank, parity, slot)
-        state = self.layout.row_views(row, None)
-        for e in self.layout.int_entries():
-            state[e.name] = self.ints[vn.slot][e.offset:e.offset + e.numel].view(e.shape)
-        return state
-
     def _forward_with(self, vn: VirtualNode, state: Optional[Dict[str, torch.Tensor]], xb: torch.Tensor) -> torch.Tensor:
         from murmura_b200.ops import fast_eval_batchnorm
         vn.model.eval()
