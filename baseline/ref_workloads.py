@@ -11,7 +11,8 @@ import numpy as np
 import torch
 from torch.utils.data import TensorDataset
 
-SHAPES = {"cifar10": ((3, 32, 32), 10), "mnist": ((784,), 10), "femnist": ((1, 28, 28), 62)}
+SHAPES = {"cifar10": ((3, 32, 32), 10), "mnist": ((784,), 10), "femnist": ((1, 28, 28), 62), "uci_har": ((561,), 6),
+          "pamap2": ((4000,), 12), "ppg_dalia": ((192,), 7)}
 
 
 def synthetic_tensors(name: str, num_samples: int, seed: int = 0, noise: float = 1.0, latent_dim: int = 32,
