@@ -110,6 +110,9 @@ class B200Config(BaseModel):
         default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
     channels_last: bool = Field(default=True, description="store 4-D weights / image shards NHWC (tensor-core conv path); "
                                 "aggregation is element-wise so the physical order is irrelevant to it")
+    gather_impl: Literal["auto", "ldg", "tma"] = Field(
+        default="auto", description="weighted_gather variant: ldg = 128-bit streaming loads (best when every source is local: L2 reuse); "
+                                    "tma = cp.async.bulk ring through shared memory (best over NVLink); auto = tma iff more than one GPU")
     placement: Literal["balanced", "contiguous"] = Field(
         default="balanced", description="virtual-node → GPU map: balanced = longest-shard-first onto the least-loaded GPU")
     unroll_round: bool = Field(default=True, description="capture ALL local steps of a node's round (epochs x batches) in one CUDA "

@@ -212,6 +212,107 @@ __global__ void wait_epoch_kernel(const uint32_t* flags, int G, uint32_t epoch, 
     wait_published(flags, G, epoch, timeout, timed_out);
 }
 
+// =============================================================================================
+// weighted_gather, TMA-bulk variant: neighbour tiles are pulled by the copy engine (`cp.async.bulk` global → shared,
+// completion on an mbarrier; SASS: UBLKCP) through an 8-stage ring, so the (NVLink) loads of the next units are in flight
+// while the CTA folds the current one — no registers are tied up by outstanding loads.  Unit = (tile of 2048 floats, source).
+// =============================================================================================
+constexpr int kBulkTile = 2048;                 // floats per unit (8 KiB)
+constexpr int kBulkStages = 8;
+constexpr int kBulkThreads = 128;               // 16 floats per thread per unit
+
+__device__ __forceinline__ uint32_t bulk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bulk_smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(kBulkThreads) weighted_gather_bulk_kernel(GatherArgs a) {
+    extern __shared__ __align__(128) uint8_t bulk_smem[];
+    __shared__ const float* s_src[kMaxRow];
+    __shared__ float s_w[kMaxRow];
+    __shared__ int s_n;
+    __shared__ __align__(8) uint64_t full_bar[kBulkStages];
+    __shared__ __align__(8) uint64_t empty_bar[kBulkStages];
+    wait_published(a.flags, a.G, a.epoch, a.timeout, a.timed_out);
+    const int v = blockIdx.y;
+    const int e0 = a.et.row_ptr[v], e1 = a.et.row_ptr[v + 1];
+    float* out = a.live + (size_t)v * a.pv.stride;
+    if (threadIdx.x == 0) {
+        const uint32_t dead = a.timed_out ? *a.timed_out : 0u;
+        int n = 0; float tot = 0.f;
+        for (int e = e0; e < e1; ++e) {
+            float w = a.w[e] * a.et.mask[e];
+            if (e != e0 && ((dead >> a.et.src_rank[e]) & 1u)) w = 0.f;
+            if (w == 0.f) continue;
+            s_src[n] = (e == e0) ? out : edge_src(a.pv, a.et, e);
+            s_w[n] = w; tot += w; ++n;
+        }
+        if (a.renorm && tot != 0.f) for (int k = 0; k < n; ++k) s_w[k] /= tot;
+        s_n = n;
+        for (int s = 0; s < kBulkStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bulk_smem_u32(&full_bar[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bulk_smem_u32(&empty_bar[s])), "r"(kBulkThreads));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (n == 1 && s_src[0] == out && s_w[0] == 1.f) return;           // keep own state untouched
+    const int len = a.len4 << 2;
+    const int ntiles = (len + kBulkTile - 1) / kBulkTile;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // tiles blockIdx.x, +gridDim.x, …
+    const long long units = (long long)my_tiles * n;
+    auto issue = [&](long long u) {                                     // thread 0 only
+        const int stage = (int)(u % kBulkStages);
+        const uint32_t use = (uint32_t)(u / kBulkStages);
+        if (use > 0) bulk_wait(&empty_bar[stage], (use - 1) & 1u);      // all 128 readers released the slot
+        const int tile = (int)blockIdx.x + (int)(u / n) * (int)gridDim.x;
+        const int k = (int)(u % n);
+        const int off = tile * kBulkTile;
+        const uint32_t bytes = (uint32_t)(min(kBulkTile, len - off) * 4);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bulk_smem_u32(&full_bar[stage])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(bulk_smem_u32(bulk_smem + stage * kBulkTile * 4)), "l"(s_src[k] + off), "r"(bytes),
+                        "r"(bulk_smem_u32(&full_bar[stage])) : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (long long u = 0; u < units && u < kBulkStages - 1; ++u) issue(u);
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long u = 0; u < units; ++u) {
+        if (threadIdx.x == 0 && u + kBulkStages - 1 < units) issue(u + kBulkStages - 1);
+        const int stage = (int)(u % kBulkStages);
+        bulk_wait(&full_bar[stage], (uint32_t)((u / kBulkStages) & 1));
+        const int k = (int)(u % n);
+        const float w = s_w[k];
+        const float4* t = reinterpret_cast<const float4*>(bulk_smem + stage * kBulkTile * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                                   // thread owns float4 #(j*128 + tid) of the tile: conflict-free
+            const float4 x = t[j * kBulkThreads + threadIdx.x];
+            acc[j].x = fmaf(w, x.x, acc[j].x); acc[j].y = fmaf(w, x.y, acc[j].y); acc[j].z = fmaf(w, x.z, acc[j].z); acc[j].w = fmaf(w, x.w, acc[j].w);
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bulk_smem_u32(&empty_bar[stage])) : "memory");
+        if (k == n - 1) {                                               // tile complete → write back in place
+            const int tile = (int)blockIdx.x + (int)(u / n) * (int)gridDim.x;
+            const int off4 = tile * (kBulkTile / 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i4 = off4 + j * kBulkThreads + threadIdx.x;
+                if (i4 < a.len4) reinterpret_cast<float4*>(out)[i4] = acc[j];
+                acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
 // int-buffer tail: ints_v = trunc(Σ_e w_tail_e · tail_src(e))  (per-aggregator rules)
 __global__ void tail_blend_kernel(float* live, PeerView pv, EdgeTable et, const float* w_tail, int Pf_pad,
                                   long long* ints, int n_int, const uint32_t* timed_out) {
@@ -699,7 +800,7 @@ void publish(Tensor live, int64_t pub_ptr, int64_t stride, int64_t V, int64_t Pf
 
 void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr,
                      Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, int64_t len, bool renorm,
-                     int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr) {
+                     int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr, bool use_tma) {
     if (V == 0) return;
     c10::cuda::CUDAGuard guard(live.device());
     mb::GatherArgs a;
@@ -709,8 +810,17 @@ void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int6
     a.w = w.data_ptr<float>(); a.len4 = (int)(len / 4); a.renorm = renorm ? 1 : 0;
     Sync s = make_sync(flags_ptr, G, epoch, timeout_ms, timed_out_ptr);
     a.flags = s.flags; a.G = s.G; a.epoch = s.epoch; a.timeout = s.timeout; a.timed_out = s.timed_out;
-    dim3 grid(grid_x_for(a.len4, mb::kThreads, (int)V), (unsigned)V);
-    mb::weighted_gather_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
+    if (use_tma) {
+        const int smem = mb::kBulkStages * mb::kBulkTile * 4;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(mb::weighted_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+        const int ntiles = (int)((len + mb::kBulkTile - 1) / mb::kBulkTile);
+        dim3 grid(std::max(1, std::min(ntiles, (148 * 3) / std::max<int>(1, (int)V))), (unsigned)V);
+        mb::weighted_gather_bulk_kernel<<<grid, mb::kBulkThreads, smem, cur_stream()>>>(a);
+    } else {
+        dim3 grid(grid_x_for(a.len4, mb::kThreads, (int)V), (unsigned)V);
+        mb::weighted_gather_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
+    }
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -13,7 +13,7 @@ void publish(Tensor live, int64_t pub_ptr, int64_t stride, int64_t V, int64_t Pf
              int64_t G, int64_t my_rank, int64_t epoch, Tensor ticket);
 void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr,
                      Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, int64_t len, bool renorm,
-                     int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
+                     int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr, bool use_tma);
 void nvls_fedavg(Tensor live, int64_t pub_local_ptr, int64_t mc_pub_ptr, int64_t stride, int64_t V, int64_t S, int64_t len,
                  int64_t N, Tensor byz, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
 void wait_epoch(Tensor anchor, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
@@ -70,7 +70,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "murmura_b200 sm_100a kernels";
     bind_arena(m);
     m.def("publish", &publish);
-    m.def("weighted_gather", &weighted_gather);
+    m.def("weighted_gather", &weighted_gather, py::arg("live"), py::arg("peer_pub_ptr"), py::arg("parity_off"), py::arg("stride"), py::arg("V"),
+          py::arg("row_ptr"), py::arg("src_rank"), py::arg("src_slot"), py::arg("mask"), py::arg("w"), py::arg("len"), py::arg("renorm"),
+          py::arg("flags_ptr"), py::arg("G"), py::arg("epoch"), py::arg("timeout_ms"), py::arg("timed_out_ptr"), py::arg("use_tma") = false);
     m.def("tail_blend", &tail_blend);
     m.def("wait_epoch", &wait_epoch);
     m.def("nvls_fedavg", &nvls_fedavg);

@@ -585,7 +585,7 @@ class B200Network:
         fp, G, ep, to, tp = self._sync_args() if sync else (0, 1, 0, 0.0, 0)
         self.ext.weighted_gather(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
                                  et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], et["w"], L.Pf_pad, renorm,
-                                 fp, G, ep, to, tp)
+                                 fp, G, ep, to, tp, self.opt.gather_impl == "tma" or (self.opt.gather_impl == "auto" and self.world > 1))
         self.kernel_launches += 1
         if L.Pi:
             self.ext.tail_blend(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,

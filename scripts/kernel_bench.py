@@ -70,6 +70,9 @@ for S, deg in ((8, 7), (20, 4), (32, 8)):
         ms = timeit(lambda: ext.weighted_gather(live, tbl.data_ptr(), 0, stride, S, et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"],
                                                 et["w"], Pf_pad, False, 0, 1, 0, 0.0, 0))
         record(f"weighted_gather S={S} deg={deg}", ms, (S * (deg + 1) + S) * Pf_pad * 4, "reads (deg+1) rows + writes 1 per node; neighbours may hit L2")
+        ms = timeit(lambda: ext.weighted_gather(live, tbl.data_ptr(), 0, stride, S, et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"],
+                                                et["w"], Pf_pad, False, 0, 1, 0, 0.0, 0, True))
+        record(f"weighted_gather_tma S={S} deg={deg}", ms, (S * (deg + 1) + S) * Pf_pad * 4, "cp.async.bulk (UBLKCP) 8-stage ring through smem")
     if only in (None, "dist"):
         d2 = torch.zeros(et["E"], device=dev); n2 = torch.zeros(S, device=dev)
         ms = timeit(lambda: ext.edge_distances(live, tbl.data_ptr(), 0, stride, S, et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"],

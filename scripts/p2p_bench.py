@@ -1,0 +1,74 @@
+"""NVLink roofline of the fused exchange+aggregate kernels (run under torchrun on >= 2 GPUs).
+
+Times `weighted_gather` (in-kernel P2P loads), the NVLS `nvls_fedavg` kernel and `edge_distances` on ResNet-18-sized rows where
+the neighbours live on PEER GPUs, with CUDA events on every rank (max over ranks), and reports the bytes that must cross
+NVLink per GPU ÷ time against the measured peer-copy bandwidth (770 GB/s per direction per GPU, B200_PROFILING.md).
+"""
+import json, os, statistics, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from murmura_b200 import Network
+from murmura_b200.config import Config
+from murmura_b200.parallel.engine import init_distributed
+from murmura_b200.utils.factories import build_aggregator_factory, build_dataset_adapter, build_model_factory
+
+NVLINK_GBS = 770.0
+rank, world, _ = init_distributed()
+n = 8 if world <= 8 else world
+
+
+def build(transport, topo, gather="ldg"):
+    cfg = Config(**{"experiment": {"name": "p2p", "rounds": 4, "seed": 1}, "topology": topo, "aggregation": {"algorithm": "fedavg"},
+                    "training": {"batch_size": 16, "lr": 0.01}, "data": {"adapter": "synthetic.cifar10", "params": {"samples_per_node": 16, "partition_method": "iid"}},
+                    "model": {"factory": "models.resnet18"}, "backend": "b200", "b200": {"transport": transport, "placement": "contiguous", "cuda_graphs": False, "gather_impl": gather}})
+    ad = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
+    return Network.from_config(cfg, mf, ad, build_aggregator_factory(cfg, mf))
+
+
+def timed(net, reps=12):
+    ts = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for r in range(reps + 3):
+        net.round_idx = r
+        flush.fill_(1)
+        # publish first (not timed), then make sure every rank's publish is visible so the timed region is the pure exchange+aggregate
+        parity = r & 1
+        neighbors, key = net._neighbors_for_round(r)
+        et = net._edge_table(neighbors, key)
+        net._publish(parity)
+        net._host_wait_epoch(); torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); net._agg_fedavg(et, parity); b.record(); torch.cuda.synchronize()
+        if r >= 3:
+            ts.append(a.elapsed_time(b))
+    ms = torch.tensor([statistics.median(ts)], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
+
+
+out = []
+for transport, topo_name, gather in (("p2p", "fully", "ldg"), ("p2p", "fully", "tma"), ("nvls", "fully", "ldg"), ("p2p", "ring", "ldg"), ("p2p", "ring", "tma")):
+    topo = {"type": topo_name, "num_nodes": n}
+    net = build(transport, topo, gather)
+    ms = timed(net)
+    L, pl = net.layout, net.placement
+    remote = sum(1 for vn in net.nodes for j in net.topology.neighbors[vn.gid] if pl.rank_of[j] != net.rank)
+    local = sum(1 for vn in net.nodes for j in net.topology.neighbors[vn.gid] if pl.rank_of[j] == net.rank) + len(net.nodes)
+    row = L.Pf_pad * 4
+    if transport == "nvls" and topo_name == "fully":
+        link_bytes = net.S * row * (world - 1) / world            # in-switch reduction: each GPU ingests S reduced rows (own share stays local)
+        note = "multimem.ld_reduce: the switch sums the ranks' copies"
+    else:
+        link_bytes = remote * row
+        note = f"{remote} remote + {local} local row reads per GPU"
+    rec = {"kernel": f"fedavg exchange+aggregate ({transport}, {topo_name}, gather={gather})", "gpus": world, "nodes": n, "ms": round(ms, 4),
+           "nvlink_GB_per_gpu": round(link_bytes / 1e9, 4), "nvlink_GBps": round(link_bytes / ms / 1e6, 1),
+           "frac_of_measured_nvlink": round(link_bytes / ms / 1e6 / NVLINK_GBS, 3), "note": note}
+    out.append(rec)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
+    net.close()
+if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open(f"gpurun_out/p2p_roofline_{world}gpu.json", "w"), indent=1)
+dist.barrier(); dist.destroy_process_group()

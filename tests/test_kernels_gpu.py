@@ -78,8 +78,9 @@ def test_publish_copy_scale_noise_tail(ext, Pf):
     assert not torch.equal(p2[2], p[2])
 
 
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("Pf,deg", [(777, 1), (4096, 3), (100003, 7), (50000, 0)])
-def test_weighted_gather_matches_oracle(ext, Pf, deg):
+def test_weighted_gather_matches_oracle(ext, Pf, deg, tma):
     S = 8
     A = FakeArena(S, Pf, seed=1)
     nbrs = [[(v + k + 1) % S for k in range(deg)] for v in range(S)]
@@ -88,7 +89,7 @@ def test_weighted_gather_matches_oracle(ext, Pf, deg):
     w = torch.rand(et["E"], generator=g).to(DEV); et["w"].copy_(w)
     live0 = A.live.clone()
     ext.weighted_gather(A.live, A.tbl.data_ptr(), A.parity_off(1), A.stride, S, et["row_ptr"], et["src_rank"], et["src_slot"],
-                        et["mask"], et["w"], A.Pf_pad, False, 0, 1, 0, 0.0, 0)
+                        et["mask"], et["w"], A.Pf_pad, False, 0, 1, 0, 0.0, 0, tma)
     rows, selfw = [], []
     wh = w.cpu().tolist()
     for v in range(S):
