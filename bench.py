@@ -32,16 +32,56 @@ METRIC = "fl_rounds_per_sec"
 
 
 class ClockSampler:
-    """nvidia-smi sampled in the background DURING the timed region (recipe's clocks line)."""
+    """SM clock + throttle reasons sampled in a background thread DURING the timed region (recipe's clocks line).
+
+    NVML is polled directly (``pynvml``, ~10 ms period: the timed region of a short run is only a few hundred ms, less than
+    one ``nvidia-smi`` start-up); ``nvidia-smi -lms`` is the fallback when the binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+            ("hw_power_brake_slowdown", 0x80))
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index: int, uuid: str = None):
+        self.rows, self.proc, self.gpu, self.uuid = [], None, gpu_index, uuid
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _poll(self, nv, h):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                self.reasons.update(name for name, bit in self.BITS if mask & bit)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            nv, h = self._nvml_handle()
+            self.source = "nvml"
+            self._thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -49,21 +89,22 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
+            r = [c.strip() for c in line.split(",")]
+            if len(r) > 8 and r[1].replace(".", "").isdigit():
+                self.sm.append(float(r[1])); self.mx.append(float(r[2]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                     if r[col].lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                        self.reasons.add(name)
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self.proc is not None:
+            self.proc.terminate()
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source,
+                "power_w_max": round(max(self.power), 1) if self.power else None}
 
 
 def _dist_env():
@@ -128,7 +169,7 @@ def run_ours(args):
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     flush = lambda: flush_buf.fill_(1)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, str(getattr(torch.cuda.get_device_properties(device), 'uuid', '') or ''))
 
     # ---- device-timed number (shards resident in HBM) -----------------------------------------
     net = make(stream_inputs=False)
@@ -219,7 +260,7 @@ def run_reference(args):
         shard_bytes = sum(len(p) for p in adapter.get_client_partitions()) * (3 * 32 * 32 * 4 + 8)
         net.train(rounds=args.warmup, local_epochs=W["local_epochs"], lr=W["lr"])
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-        sampler = ClockSampler(local_rank); sampler.start()
+        sampler = ClockSampler(local_rank, str(getattr(torch.cuda.get_device_properties(device), 'uuid', '') or '')); sampler.start()
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
         pairs = []

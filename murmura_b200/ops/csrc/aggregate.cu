@@ -228,7 +228,7 @@ __device__ __forceinline__ void bulk_wait(uint64_t* bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bulk_smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (1u << 28)) __trap();
     }
 }
 
@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(kBulkThreads) weighted_gather_bulk_kernel(Gath
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bulk_smem_u32(&empty_bar[s])), "r"(kBulkThreads));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");               // rows were produced / acquired through the generic proxy
     }
     __syncthreads();
     const int n = s_n;

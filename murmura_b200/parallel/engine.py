@@ -1052,7 +1052,22 @@ class B200Network:
             self._dmtt_score_and_update(et, parity)
         plan = getattr(self, f"_agg_{self.family}", self._agg_generic)
         self._last_et = et
+        self._account_traffic(et)
         plan(et, parity)
+
+    _FILTER_ROW_PASSES = {"balance": 1.0, "ubar": 1.0}        # families whose filter streams every neighbour row once more
+
+    def _account_traffic(self, et) -> None:
+        """Algorithmic bytes of this round's exchange+aggregate on this GPU, assuming every edge is accepted
+        (publish: read+write V rows; filter pass; gather: one read per edge + one write per node). Feeds ``perf_summary``."""
+        rk = et["host_rank"]
+        edges = len(rk)
+        remote = sum(1 for r in rk if r != self.rank)
+        row = self.layout.Pf_pad * 4
+        passes = 1.0 + self._FILTER_ROW_PASSES.get(self.family, 0.0)
+        extra = self.V if self.family == "sketchguard" else (self.N / max(self.world, 1) if self.family == "krum" else 0.0)
+        self.timers["hbm_bytes"] = self.timers.get("hbm_bytes", 0.0) + row * (3 * self.V + passes * (edges - remote) + extra)
+        self.timers["nvlink_bytes"] = self.timers.get("nvlink_bytes", 0.0) + row * passes * remote
 
     # =========================================================================================
     # evaluation
@@ -1291,8 +1306,16 @@ class B200Network:
         if not t["rounds"] or not self.opt.profile:
             return f"{int(t['rounds'])} rounds on {self.world} GPU(s); set b200.profile: true for the per-phase split"
         r = t["rounds"]
-        return (f"train {t['train_ms'] / r:.2f} ms  aggregate {t['aggregate_ms'] / r:.3f} ms  eval {t['eval_ms'] / r:.2f} ms "
+        line = (f"train {t['train_ms'] / r:.2f} ms  aggregate {t['aggregate_ms'] / r:.3f} ms  eval {t['eval_ms'] / r:.2f} ms "
                 f"per round ({self.world} GPU(s))")
+        if t["aggregate_ms"] > 0 and t.get("hbm_bytes"):
+            peak = _measured_hbm_gbs()
+            hbm = t["hbm_bytes"] / t["aggregate_ms"] / 1e6
+            line += f"; exchange+aggregate ≈ {hbm:.0f} GB/s HBM ({hbm / peak:.2f} of {peak:.0f} GB/s measured)"
+            if t.get("nvlink_bytes"):
+                line += f" + {t['nvlink_bytes'] / t['aggregate_ms'] / 1e6:.0f} GB/s over NVLink"
+            line += " [algorithmic bytes, all edges accepted; includes flag waits and filter kernels]"
+        return line
 
     def state_dict_of(self, gid: int) -> Dict[str, torch.Tensor]:
         vn = next(v for v in self.nodes if v.gid == gid)
@@ -1340,6 +1363,16 @@ class B200Network:
         if self.world > 1:
             _dist().barrier()
         self.arena.close()
+
+
+def _measured_hbm_gbs() -> float:
+    """Copy bandwidth from the driver-written ``MEASURED_PEAKS.json`` (fallback: the profiling recipe's 6567 GB/s)."""
+    try:
+        import json
+        root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        return float(json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        return 6567.0
 
 
 def copy_aggregator(agg):

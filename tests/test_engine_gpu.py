@@ -173,6 +173,21 @@ def test_end_to_end_training_and_contract(capsys):
         net.close()
 
 
+def test_profile_mode_reports_phase_split_and_roofline_fraction():
+    cfg = _cfg("balance", n=6, rounds=3, b200={"profile": True})
+    net, _, _ = _build(cfg)
+    try:
+        net.train(rounds=3, local_epochs=1, lr=0.05)
+        line = net.perf_summary()
+        assert re.search(r"train \d+\.\d+ ms  aggregate \d+\.\d+ ms  eval \d+\.\d+ ms", line)
+        assert "of" in line and "GB/s measured" in line
+        row = net.layout.Pf_pad * 4                       # k-regular(2): 3 edges per node incl. self; balance streams neighbours twice
+        assert net.timers["hbm_bytes"] == pytest.approx(3 * row * (3 * 6 + 2.0 * 18))
+        assert net.timers.get("nvlink_bytes", 0.0) == 0.0
+    finally:
+        net.close()
+
+
 def test_graphs_match_eager_and_simulation_statistically():
     accs = {}
     data = {"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}}
