@@ -14,6 +14,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from murmura_b200.ops import bn_act
+
 
 class MLP(nn.Module):
     """Plain ``in → hidden… → classes`` ReLU MLP (default 784-200-10, P = 159,010)."""
@@ -70,7 +72,19 @@ class EvidentialMLP(nn.Module):
         self.dropout = dropout
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.evidential_head(self.feature_extractor(x))
+        # Same module sequence as ``self.feature_extractor(x)``; BatchNorm1d → ReLU pairs go through ``ops.bn_act``
+        # (one fused launch per direction on sm_100a, the stock ops anywhere else).
+        mods = list(self.feature_extractor)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.BatchNorm1d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                x = bn_act(x, m, relu=True)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return self.evidential_head(x)
 
     def predict(self, x: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
         alpha = self.forward(x)

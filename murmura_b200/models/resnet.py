@@ -9,6 +9,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from murmura_b200.ops import bn_act
+
 
 class BasicBlock(nn.Module):
     def __init__(self, inplanes: int, planes: int, stride: int = 1):
@@ -24,10 +26,13 @@ class BasicBlock(nn.Module):
                                             nn.BatchNorm2d(planes))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return self.relu(out + identity)
+        # bn_act = relu(bn(x) [+ identity]) — one fused launch per direction on sm_100a, stock ops elsewhere
+        if self.downsample is None:
+            identity = x
+        else:
+            identity = bn_act(self.downsample[0](x), self.downsample[1], relu=False)
+        out = bn_act(self.conv1(x), self.bn1)
+        return bn_act(self.conv2(out), self.bn2, residual=identity)
 
 
 class ResNet18(nn.Module):
@@ -48,6 +53,6 @@ class ResNet18(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(self.conv1(x), self.bn1))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(self.avgpool(x).flatten(1))

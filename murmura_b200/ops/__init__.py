@@ -23,7 +23,7 @@ _HERE = Path(__file__).resolve().parent
 _SRC = _HERE / "csrc"
 _BUILD = _HERE / "_build"
 _NAME = "murmura_b200_ext"
-_SOURCES = ["bindings.cpp", "arena.cu", "aggregate.cu", "train.cu", "gram_tcgen05.cu", "mlp_tcgen05.cu", "dmtt.cu"]
+_SOURCES = ["bindings.cpp", "arena.cu", "aggregate.cu", "train.cu", "gram_tcgen05.cu", "mlp_tcgen05.cu", "dmtt.cu", "bn_train.cu"]
 _CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--use_fast_math",
                "-std=c++17", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -128,6 +128,69 @@ def evidential_loss(alpha: torch.Tensor, targets: torch.Tensor, lam) -> torch.Te
     return _EvidentialLossFn.apply(alpha, targets, lam)
 
 
+# ---- fused BatchNorm (+residual) (+ReLU): training fwd/bwd in one launch each ------------------------
+
+class _BNActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, residual, momentum, eps, relu):
+        y, mean, invstd = ext().bn_act_fwd(x, residual, weight, bias, running_mean, running_var, nbt, float(momentum), float(eps), bool(relu))
+        ctx.save_for_backward(x, y, weight, mean, invstd)
+        ctx.relu, ctx.has_res = bool(relu), residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        fmt = torch.channels_last if x.dim() == 4 else torch.contiguous_format
+        dx, dw, db, dres = ext().bn_act_bwd(dy.contiguous(memory_format=fmt), x, y, weight, mean, invstd, ctx.relu,
+                                            ctx.has_res and ctx.needs_input_grad[6])
+        return dx, dw, db, None, None, None, (dres if ctx.has_res else None), None, None, None
+
+
+_fused_bn = os.environ.get("MURMURA_B200_FUSED_BN", "1") != "0"
+
+
+def set_fused_bn(enabled: bool) -> None:
+    """Globally enable/disable the fused BatchNorm path of :func:`bn_act` (``b200.fused_bn``)."""
+    global _fused_bn
+    _fused_bn = bool(enabled)
+
+
+def _bn_layout_ok(x: torch.Tensor) -> bool:
+    if x.dim() == 2:
+        return x.is_contiguous()
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def bn_act_fusable(x: torch.Tensor, bn) -> bool:
+    """True when ``bn_act`` will take the fused sm_100a path for this input/module."""
+    return (_fused_bn and x.is_cuda and x.dtype == torch.float32 and bn.affine and bn.track_running_stats and bn.momentum is not None
+            and x.dim() in (2, 4) and x.shape[1] % 4 == 0 and _bn_layout_ok(x) and available()
+            and (not bn.training or x.numel() // x.shape[1] >= 2))
+
+
+def bn_act(x: torch.Tensor, bn, residual: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
+    """``relu(bn(x) + residual)`` of an ``nn.BatchNorm{1,2}d`` module ``bn``.
+
+    On CUDA (fp32, [B,C] or channels_last activations) the training forward and backward are ONE launch each
+    (``bn_train.cu``: thread-block-cluster reduction through distributed shared memory; running statistics and
+    ``num_batches_tracked`` updated in the same kernel) and evaluation is one ``bn_eval`` launch; anything else falls back
+    to the stock PyTorch ops with identical semantics."""
+    if bn_act_fusable(x, bn):
+        if residual is not None and (residual.dtype != x.dtype or residual.stride() != x.stride()):
+            residual = torch.empty_like(x).copy_(residual)
+        if bn.training:
+            return _BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, residual,
+                                  bn.momentum, bn.eps, relu)
+        if not torch.is_grad_enabled():
+            return ext().bn_eval(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, float(bn.eps), bool(relu), residual)
+    import torch.nn.functional as F
+    out = torch.nn.modules.batchnorm._BatchNorm.forward(bn, x)
+    if residual is not None:
+        out = out + residual
+    return F.relu(out) if relu else out
+
+
 class fast_eval_batchnorm:
     """Context manager: route inference-mode ``F.batch_norm`` on fp32 CUDA tensors to ``train.cu::bn_eval_kernel``.
 
@@ -154,4 +217,4 @@ class fast_eval_batchnorm:
         return False
 
 
-__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss", "fast_eval_batchnorm"]
+__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss", "fast_eval_batchnorm", "bn_act", "bn_act_fusable", "set_fused_bn"]

@@ -47,7 +47,11 @@ void trust_filter(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, T
 // train.cu
 void sgd_step(Tensor live, int64_t stride, Tensor grad, int64_t gstride, int64_t slot0, int64_t nslots, int64_t n, double lr);
 void sgd_multi(std::vector<Tensor> params, std::vector<Tensor> grads, double lr);
-Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps, bool relu);
+Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps, bool relu,
+               c10::optional<Tensor> residual);
+std::vector<Tensor> bn_act_fwd(Tensor x, c10::optional<Tensor> residual, Tensor gamma, Tensor beta, c10::optional<Tensor> rmean,
+                               c10::optional<Tensor> rvar, c10::optional<Tensor> nbt, double momentum, double eps, bool relu);
+std::vector<Tensor> bn_act_bwd(Tensor dy, Tensor x, Tensor y, Tensor gamma, Tensor save_mean, Tensor save_invstd, bool relu, bool want_dres);
 void ce_eval(Tensor logits, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats);
 void dirichlet_eval(Tensor alpha, Tensor targets, c10::optional<Tensor> n_valid, Tensor stats);
 std::vector<Tensor> evidential_loss_fwd_bwd(Tensor alpha, Tensor targets, double lam, c10::optional<Tensor> lam_t);
@@ -89,7 +93,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("trust_filter", &trust_filter);
     m.def("sgd_step", &sgd_step);
     m.def("sgd_multi", &sgd_multi);
-    m.def("bn_eval", &bn_eval);
+    m.def("bn_eval", &bn_eval, py::arg("x"), py::arg("mean"), py::arg("var"), py::arg("gamma"), py::arg("beta"), py::arg("eps"), py::arg("relu"),
+          py::arg("residual") = py::none());
+    m.def("bn_act_fwd", &bn_act_fwd, "fused training BatchNorm (+residual) (+ReLU), cluster/DSMEM reduction");
+    m.def("bn_act_bwd", &bn_act_bwd);
     m.def("ce_eval", &ce_eval);
     m.def("dirichlet_eval", &dirichlet_eval);
     m.def("evidential_loss_fwd_bwd", &evidential_loss_fwd_bwd);

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
 // `inner` = elements between consecutive channel indices: 1 for channels_last (NHWC) tensors, H*W for NCHW / [B,C].
 __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
                                                       const float* __restrict__ var, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, float eps, long long n, int C, int inner, int relu) {
+                                                      const float* __restrict__ beta, float eps, long long n, int C, int inner, int relu,
+                                                      const float* __restrict__ res) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     if (inner == 1 && (C & 3) == 0) {                        // NHWC, 4 consecutive channels per thread
         const long long n4 = n >> 2;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
             const float4 b = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             v.x = (v.x - m.x) * rsqrtf(s2.x + eps) * g.x + b.x; v.y = (v.y - m.y) * rsqrtf(s2.y + eps) * g.y + b.y;
             v.z = (v.z - m.z) * rsqrtf(s2.z + eps) * g.z + b.z; v.w = (v.w - m.w) * rsqrtf(s2.w + eps) * g.w + b.w;
+            if (res) { const float4 t = reinterpret_cast<const float4*>(res)[i]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             reinterpret_cast<float4*>(y)[i] = v;
         }
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = (int)((i / inner) % C);
         float v = (x[i] - mean[c]) * rsqrtf(var[c] + eps) * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
+        if (res) v += res[i];
         y[i] = relu ? fmaxf(v, 0.f) : v;
     }
 }
@@ -247,7 +250,8 @@ void sgd_multi(std::vector<Tensor> params, std::vector<Tensor> grads, double lr)
     }
 }
 
-Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps, bool relu) {
+Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps, bool relu,
+               c10::optional<Tensor> residual) {
     c10::cuda::CUDAGuard guard(x.device());
     TORCH_CHECK(x.dtype() == torch::kFloat32 && x.dim() >= 2);
     const int C = (int)x.size(1);
@@ -259,10 +263,16 @@ Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c
     Tensor y = torch::empty_like(xin);
     const long long n = xin.numel();
     if (n == 0) return y;
+    const float* res = nullptr;
+    Tensor rin;
+    if (residual.has_value() && residual->defined()) {              // must share xin's physical layout
+        rin = residual->strides() == xin.strides() ? *residual : torch::empty_like(xin).copy_(*residual);
+        res = rin.data_ptr<float>();
+    }
     const int blocks = (int)std::min<long long>(148 * 8, (n / 4 + 255) / 256 + 1);
     mb::bn_eval_kernel<<<blocks, 256, 0, cur_stream()>>>(xin.data_ptr<float>(), y.data_ptr<float>(), mean.data_ptr<float>(), var.data_ptr<float>(),
         gamma.has_value() && gamma->defined() ? gamma->data_ptr<float>() : nullptr, beta.has_value() && beta->defined() ? beta->data_ptr<float>() : nullptr,
-        (float)eps, n, C, inner, relu ? 1 : 0);
+        (float)eps, n, C, inner, relu ? 1 : 0, res);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return y;
 }

@@ -35,6 +35,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from murmura_b200 import ops as _ops
 from murmura_b200.aggregation.balance import decayed_factor
 from murmura_b200.core.network import new_history, record_round
 from murmura_b200.parallel.arena import Placement, StateLayout, SymmetricArena
@@ -356,6 +357,7 @@ class B200Network:
     def _apply_math_mode(self) -> None:
         mode = self.opt.compute_dtype
         torch.backends.cudnn.benchmark = True
+        _ops.set_fused_bn(self.opt.fused_bn and mode != "bf16")
         if mode in ("tf32", "bf16"):
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True

@@ -174,3 +174,22 @@ def test_state_layout_and_channels_last_permutation():
     assert all(int(b.slot_of[g]) == b.local_nodes(int(b.rank_of[g])).index(g) for g in range(8))
     c = Placement(8, 2)
     assert [sum(w[g] for g in c.local_nodes(r)) for r in range(2)] == [38, 22]
+
+
+def test_evidential_mlp_forward_equals_its_sequential_definition():
+    """forward() walks the Sequential itself (BatchNorm→ReLU pairs go through ops.bn_act); on CPU it must equal the plain
+    Sequential composition, in train mode (batch statistics, running-stat updates) and eval mode."""
+    import copy
+    import torch
+    from murmura_b200.models.mlp import EvidentialHARClassifier
+    torch.manual_seed(0)
+    a = EvidentialHARClassifier(input_dim=24, hidden_dims=(16, 8), num_classes=5, dropout=0.0)
+    b = copy.deepcopy(a)
+    x = torch.randn(12, 24)
+    ya = a(x)
+    yb = b.evidential_head(b.feature_extractor(x))
+    assert torch.allclose(ya, yb, atol=1e-6)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.allclose(va.float(), vb.float(), atol=1e-6), ka
+    a.eval(); b.eval()
+    assert torch.allclose(a(x), b.evidential_head(b.feature_extractor(x)), atol=1e-6)

@@ -539,3 +539,70 @@ def test_grouped_linear_tcgen05(ext, K, N, act, bn):
         for i in range(G):
             ref = R.dirichlet_stats(Y[i, :Ms[i]].cpu(), tg[i].cpu()) if act == 2 else R.ce_stats(Y[i, :Ms[i]].cpu(), tg[i].cpu())
             assert torch.allclose(stats[i, :len(ref)].cpu(), ref.float(), rtol=3e-4, atol=1e-3)
+
+
+# ---- fused BatchNorm (+residual) (+ReLU) training kernels (bn_train.cu) -----------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 64, 16, 16), (64, 64, 8, 8), (64, 128, 4, 4), (64, 512, 1, 1), (7, 20, 5, 3), (32, 256), (3, 36)])
+@pytest.mark.parametrize("relu,with_res", [(True, False), (True, True), (False, False)])
+def test_bn_act_training_matches_stock_batchnorm(ext, shape, relu, with_res):
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from murmura_b200 import ops
+    torch.manual_seed(5)
+    C = shape[1]
+    bn_cls = nn.BatchNorm2d if len(shape) == 4 else nn.BatchNorm1d
+    fmt = torch.channels_last if len(shape) == 4 else torch.contiguous_format
+    ref, fused = bn_cls(C).cuda(), bn_cls(C).cuda()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5); ref.bias.normal_(); ref.running_mean.normal_(); ref.running_var.uniform_(0.5, 2.0)
+    fused.load_state_dict(ref.state_dict())
+    x0 = (torch.randn(*shape, device="cuda") * 2.0 + 3.0).contiguous(memory_format=fmt)        # non-zero mean: exercises the shifted sums
+    r0 = torch.randn(*shape, device="cuda").contiguous(memory_format=fmt) if with_res else None
+    g = torch.randn(*shape, device="cuda").contiguous(memory_format=fmt)
+    outs = []
+    for mod, use_fused in ((ref, False), (fused, True)):
+        x = x0.clone().requires_grad_(True)
+        r = r0.clone().requires_grad_(True) if with_res else None
+        if use_fused:
+            assert ops.bn_act_fusable(x, mod)
+            y = ops.bn_act(x, mod, residual=r, relu=relu)
+        else:
+            y = mod(x)
+            if with_res:
+                y = y + r
+            y = F.relu(y) if relu else y
+        y.backward(g)
+        outs.append((y.detach(), x.grad, mod.weight.grad, mod.bias.grad, r.grad if with_res else None,
+                     mod.running_mean.clone(), mod.running_var.clone(), int(mod.num_batches_tracked)))
+    a, b = outs
+    names = ["y", "dx", "dgamma", "dbeta", "dres", "running_mean", "running_var"]
+    for name, u, v in zip(names, a[:7], b[:7]):
+        if u is None:
+            continue
+        scale = float(u.abs().max()) + 1e-6
+        assert float((u - v).abs().max()) / scale < 2e-4, name
+    assert a[7] == b[7] == 1
+    assert b[0].stride() == x0.stride()
+
+
+def test_bn_act_eval_and_fallbacks(ext):
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from murmura_b200 import ops
+    torch.manual_seed(6)
+    bn = nn.BatchNorm2d(32).cuda()
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    bn.eval()
+    x = torch.randn(9, 32, 6, 6, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x)
+    with torch.no_grad():
+        got = ops.bn_act(x, bn, residual=r, relu=True)
+        want = F.relu(bn(x) + r)
+    assert float((got - want).abs().max()) < 1e-5
+    # NCHW-contiguous input is not fusable: identical semantics through the stock ops
+    xn = torch.randn(9, 32, 6, 6, device="cuda")
+    assert not ops.bn_act_fusable(xn, bn)
+    with torch.no_grad():
+        assert torch.equal(ops.bn_act(xn, bn, relu=False), bn(xn))
+    assert int(bn.num_batches_tracked) == 0
