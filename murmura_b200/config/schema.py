@@ -110,6 +110,7 @@ class B200Config(BaseModel):
         default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
     channels_last: bool = Field(default=True, description="store 4-D weights / image shards NHWC (tensor-core conv path); "
                                 "aggregation is element-wise so the physical order is irrelevant to it")
+    split_backward: bool = Field(default=True, description="compute weight gradients on a side stream (parallel graph branch) so only the data-gradient chain is on the critical path")
     fused_bn: bool = Field(default=True, description="fused BatchNorm(+residual)(+ReLU) training kernels (cluster/DSMEM reduction) in the bundled models")
     gather_impl: Literal["auto", "ldg", "tma"] = Field(
         default="auto", description="weighted_gather variant: ldg = 128-bit streaming loads (best when every source is local: L2 reuse); "

@@ -87,6 +87,7 @@ class VirtualNode:
     steps_per_replay: int = 1
     eval_graph: Any = None
     graph_key: Any = None
+    split_bwd: Any = None   # SplitBackward of this node (side stream for weight gradients)
 
 
 def mlp_plan(model: nn.Module, layout: StateLayout) -> Optional[List[Dict[str, Any]]]:
@@ -438,22 +439,35 @@ class B200Network:
     def _inputs(vn: VirtualNode, x: torch.Tensor) -> torch.Tensor:
         return x.permute(0, 3, 1, 2) if vn.nhwc else x        # zero-copy logical NCHW view of the NHWC shard
 
+    def _split_backward(self, vn: VirtualNode):
+        if not self.opt.split_backward or self.opt.compute_dtype == "bf16":
+            return None
+        sb = getattr(vn, "split_bwd", None)
+        if sb is None:
+            from murmura_b200.parallel.split_backward import SplitBackward
+            sb = vn.split_bwd = SplitBackward(self.device)
+        return sb
+
     def _train_step(self, vn: VirtualNode, lr: float) -> None:
         pos = vn.step * vn.eb + vn.arange
         idx = vn.perm_buf.index_select(0, pos)
         xb = self._inputs(vn, vn.X.index_select(0, idx)); yb = vn.y.index_select(0, idx)
         for p in vn.params:
             p.grad = None                                      # autograd hands us its own grad buffers: no accumulate pass
-        with self._autocast():
+        sb = self._split_backward(vn)
+        with self._autocast(), (sb if sb is not None else nullcontext()):
             out = vn.model(xb)
         loss = self._loss(out, yb)
         loss.backward()
-        grads = []
-        for p in vn.params:
-            g = p.grad
-            if g.stride() != p.stride() or g.dtype != p.dtype:
-                g = torch.empty_like(p).copy_(g)
-            grads.append(g)
+        if sb is not None:
+            grads = sb.join(vn.params)                         # weight gradients were computed on the side stream
+        else:
+            grads = []
+            for p in vn.params:
+                g = p.grad
+                if g.stride() != p.stride() or g.dtype != p.dtype:
+                    g = torch.empty_like(p).copy_(g)
+                grads.append(g)
         self.ext.sgd_multi(vn.params, grads, lr)              # one launch: θ -= lr·g for every tensor of the node
         vn.step += 1
         vn.loss_sum += loss.detach()

@@ -52,8 +52,11 @@ for shape in [(64, 64, 16, 16), (64, 64, 8, 8), (64, 128, 4, 4), (64, 256, 2, 2)
     out.append(rec); print(json.dumps(rec), flush=True)
 
 # whole ResNet-18 SGD step (batch 64, 32x32), one stream, CUDA graph of 4 steps
-for fused_on in (False, True):
+from murmura_b200.parallel.split_backward import SplitBackward
+from contextlib import nullcontext
+for fused_on, split_on in ((False, False), (True, False), (True, True)):
     ops.set_fused_bn(fused_on)
+    sb = SplitBackward(dev) if split_on else None
     torch.manual_seed(0)
     m = ResNet18().to(dev).to(memory_format=torch.channels_last).train()
     params = [p for p in m.parameters()]
@@ -62,12 +65,14 @@ for fused_on in (False, True):
     def step():
         for p in params:
             p.grad = None
-        F.cross_entropy(m(X), Y).backward()
-        with torch.no_grad():
-            torch._foreach_add_(params, [p.grad for p in params], alpha=-0.01)
+        with (sb if sb is not None else nullcontext()):
+            out = m(X)
+        F.cross_entropy(out, Y).backward()
+        grads = sb.join(params) if sb is not None else [p.grad for p in params]
+        ext.sgd_multi(params, grads, 0.01)
 
     us = graph_time(step, iters=20, inner=4)
-    rec = {"resnet18_sgd_step_batch64": "fused_bn" if fused_on else "stock", "us_per_step": round(us, 1)}
+    rec = {"resnet18_sgd_step_batch64": ("fused_bn" if fused_on else "stock") + ("+split_backward" if split_on else ""), "us_per_step": round(us, 1)}
     out.append(rec); print(json.dumps(rec), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bn_act_bench.json", "w"), indent=1)
