@@ -49,7 +49,8 @@ def main():
             if KEY.match(op):
                 cnt[op] += 1
         with open(os.path.join(OUT, label.replace("<", "_").replace(">", "") + ".sass"), "w") as f:
-            f.write(f"\t\tFunction : {mangled}\n" + "\n".join(lines) + "\n")
+            body = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip() for l in lines]           # drop the encoding column
+            f.write(f"\t\tFunction : {mangled}\n" + "\n".join(l for l in body if l.strip()) + "\n")
         sig = re.compile(r"^(UTC|LDTM|STTM|UTMA|UBLKCP|SYNCS|UCGABAR|CGAERRBAR|MAPA|LDGMC|QSPC|F2FP)|STRONG\.SYS|\.NA\.")
         first = sorted((kv for kv in cnt.items() if sig.search(kv[0])), key=lambda kv: (-kv[1], kv[0]))
         rest = sorted((kv for kv in cnt.items() if not sig.search(kv[0])), key=lambda kv: (-kv[1], kv[0]))
