@@ -141,6 +141,15 @@ def _timed_rounds(run_round, steps: int, device, flush):
     return sum(a.elapsed_time(b) for a, b in pairs)
 
 
+def _b200_overrides(args):
+    """``--b200 key=value …`` → extra ``b200:`` options (ablations: split_backward=false, fused_bn=false, gather_impl=ldg …)."""
+    out = {}
+    for kv in args.b200 or []:
+        k, v = kv.split("=", 1)
+        out[k] = {"true": True, "false": False}.get(v.lower(), int(v) if v.lstrip("-").isdigit() else v)
+    return out
+
+
 def run_ours(args):
     import torch
     from murmura_b200 import Network
@@ -162,7 +171,7 @@ def run_ours(args):
             "data": {"adapter": "synthetic.cifar10", "params": {"samples_per_node": W["samples_per_node"],
                                                                 "partition_method": "dirichlet", "alpha": W["alpha"]}},
             "model": {"factory": "models.resnet18", "params": {"num_classes": 10}},
-            "backend": "b200", "b200": {"stream_inputs": stream_inputs, "streams": 8, "transport": args.transport},
+            "backend": "b200", "b200": {"stream_inputs": stream_inputs, "streams": 8, "transport": args.transport, **_b200_overrides(args)},
         })
         adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
         return Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf), device=device)
@@ -300,6 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--b200", nargs="*", default=[], help="extra b200 engine options as key=value (ablations)")
     ap.add_argument("--transport", choices=["p2p", "nvls", "nccl"], default="p2p",
                     help="p2p: in-kernel peer loads (default); nvls: full-mesh FedAvg through multimem.ld_reduce; nccl: baseline")
     args = ap.parse_args()

@@ -7,7 +7,7 @@ Blackwell engine (GPU count, transport, CUDA graphs, compute dtype, sketch preci
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Literal, Optional
+from typing import Union, Any, Dict, Literal, Optional
 
 from pydantic import BaseModel, ConfigDict, Field
 
@@ -110,7 +110,9 @@ class B200Config(BaseModel):
         default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
     channels_last: bool = Field(default=True, description="store 4-D weights / image shards NHWC (tensor-core conv path); "
                                 "aggregation is element-wise so the physical order is irrelevant to it")
-    split_backward: bool = Field(default=True, description="compute weight gradients on a side stream (parallel graph branch) so only the data-gradient chain is on the critical path")
+    split_backward: Union[bool, Literal["auto"]] = Field(
+        default="auto", description="compute weight gradients on a side stream (parallel graph branch) so only the data-gradient chain is on "
+                                    "the critical path; auto = only when a GPU hosts at most 2 nodes (more streams than hardware queues serialise)")
     fused_bn: bool = Field(default=True, description="fused BatchNorm(+residual)(+ReLU) training kernels (cluster/DSMEM reduction) in the bundled models")
     gather_impl: Literal["auto", "ldg", "tma"] = Field(
         default="auto", description="weighted_gather variant: ldg = 128-bit streaming loads (best when every source is local: L2 reuse); "

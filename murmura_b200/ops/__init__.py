@@ -29,6 +29,7 @@ _CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 
 _ext = None
 _load_error: Optional[str] = None
+counters = {"launches": 0}          # launches of our kernels issued through the Python wrappers below (engine's launch accounting)
 
 
 def _source_digest() -> str:
@@ -128,12 +129,32 @@ def evidential_loss(alpha: torch.Tensor, targets: torch.Tensor, lam) -> torch.Te
     return _EvidentialLossFn.apply(alpha, targets, lam)
 
 
+class _CELossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits: torch.Tensor, targets: torch.Tensor, loss_acc):
+        loss, grad = ext().ce_loss_fwd_bwd(logits.contiguous().float(), targets.contiguous(), loss_acc)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def ce_loss(logits: torch.Tensor, targets: torch.Tensor, loss_acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Mean softmax cross-entropy, forward+backward in one launch (``train.cu::ce_loss_kernel``); ``loss_acc`` (0-dim fp32
+    CUDA tensor) is incremented by the loss inside the kernel."""
+    return _CELossFn.apply(logits, targets, loss_acc)
+
+
 # ---- fused BatchNorm (+residual) (+ReLU): training fwd/bwd in one launch each ------------------------
 
 class _BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, nbt, residual, momentum, eps, relu):
         y, mean, invstd = ext().bn_act_fwd(x, residual, weight, bias, running_mean, running_var, nbt, float(momentum), float(eps), bool(relu))
+        counters["launches"] += 1
         ctx.save_for_backward(x, y, weight, mean, invstd)
         ctx.relu, ctx.has_res = bool(relu), residual is not None
         return y
@@ -142,6 +163,7 @@ class _BNActFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, y, weight, mean, invstd = ctx.saved_tensors
         fmt = torch.channels_last if x.dim() == 4 else torch.contiguous_format
+        counters["launches"] += 1
         dx, dw, db, dres = ext().bn_act_bwd(dy.contiguous(memory_format=fmt), x, y, weight, mean, invstd, ctx.relu,
                                             ctx.has_res and ctx.needs_input_grad[6])
         return dx, dw, db, None, None, None, (dres if ctx.has_res else None), None, None, None
@@ -183,6 +205,7 @@ def bn_act(x: torch.Tensor, bn, residual: Optional[torch.Tensor] = None, relu: b
             return _BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, residual,
                                   bn.momentum, bn.eps, relu)
         if not torch.is_grad_enabled():
+            counters["launches"] += 1
             return ext().bn_eval(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, float(bn.eps), bool(relu), residual)
     import torch.nn.functional as F
     out = torch.nn.modules.batchnorm._BatchNorm.forward(bn, x)
@@ -217,4 +240,4 @@ class fast_eval_batchnorm:
         return False
 
 
-__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss", "fast_eval_batchnorm", "bn_act", "bn_act_fusable", "set_fused_bn"]
+__all__ = ["available", "build_extension", "load", "load_error", "ext", "evidential_loss", "ce_loss", "fast_eval_batchnorm", "bn_act", "bn_act_fusable", "set_fused_bn"]

@@ -49,6 +49,8 @@ void sgd_step(Tensor live, int64_t stride, Tensor grad, int64_t gstride, int64_t
 void sgd_multi(std::vector<Tensor> params, std::vector<Tensor> grads, double lr);
 Tensor bn_eval(Tensor x, Tensor mean, Tensor var, c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps, bool relu,
                c10::optional<Tensor> residual);
+std::vector<Tensor> ce_loss_fwd_bwd(Tensor logits, Tensor targets, c10::optional<Tensor> loss_acc);
+std::vector<Tensor> gather_batch(Tensor X, Tensor y, Tensor perm, Tensor step, Tensor ticket, int64_t eb);
 std::vector<Tensor> bn_act_fwd(Tensor x, c10::optional<Tensor> residual, Tensor gamma, Tensor beta, c10::optional<Tensor> rmean,
                                c10::optional<Tensor> rvar, c10::optional<Tensor> nbt, double momentum, double eps, bool relu);
 std::vector<Tensor> bn_act_bwd(Tensor dy, Tensor x, Tensor y, Tensor gamma, Tensor save_mean, Tensor save_invstd, bool relu, bool want_dres);
@@ -97,6 +99,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("residual") = py::none());
     m.def("bn_act_fwd", &bn_act_fwd, "fused training BatchNorm (+residual) (+ReLU), cluster/DSMEM reduction");
     m.def("bn_act_bwd", &bn_act_bwd);
+    m.def("ce_loss_fwd_bwd", &ce_loss_fwd_bwd, "fused softmax cross-entropy forward+backward (+ running-loss accumulator)");
+    m.def("gather_batch", &gather_batch, "mini-batch gather through a device-side permutation; advances the step counter");
     m.def("ce_eval", &ce_eval);
     m.def("dirichlet_eval", &dirichlet_eval);
     m.def("evidential_loss_fwd_bwd", &evidential_loss_fwd_bwd);

@@ -204,6 +204,68 @@ __global__ void evidential_loss_kernel(const float* __restrict__ alpha, const lo
     if (lane == 0) atomicAdd(loss_out, (mse + lam * kl) * invB);
 }
 
+// ---- fused softmax cross-entropy: forward + backward + running-loss accumulator, ONE launch ---------------------------
+// Replaces log_softmax / nll_loss / their two backward kernels / the `loss_sum += loss` add of a training step.
+// One CTA (the batch of a federated client is tens of rows): warp per row, block reduction, no zero-init launch, no atomics.
+__global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, int B, int C,
+                                                      float* __restrict__ loss_out, float* __restrict__ loss_acc, float* __restrict__ grad) {
+    __shared__ float wsum[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float invB = 1.f / (float)B;
+    float local = 0.f;
+    for (int r = warp; r < B; r += 8) {
+        const float* z = logits + (size_t)r * C;
+        float* g = grad + (size_t)r * C;
+        const int t = (int)targets[r];
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += __expf(z[c] - mx);
+        se = warp_sum(se);
+        const float lse = mx + __logf(se), inv = 1.f / se;
+        for (int c = lane; c < C; c += 32) g[c] = (__expf(z[c] - mx) * inv - (c == t ? 1.f : 0.f)) * invB;
+        if (lane == 0) local += lse - z[t];
+    }
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += wsum[w];
+        tot *= invB;
+        *loss_out = tot;
+        if (loss_acc) *loss_acc += tot;
+    }
+}
+
+// ---- mini-batch gather: xb[r] = X[perm[step·eb + r]], yb likewise; the last CTA advances the device-side step counter ----
+// Replaces 2 index arithmetic kernels + 3 index_select + the counter increment of a training step.
+__global__ void __launch_bounds__(256) gather_batch_kernel(const float* __restrict__ X, const long long* __restrict__ y,
+                                                           const long long* __restrict__ perm, long long* __restrict__ step,
+                                                           unsigned int* __restrict__ ticket, int eb, long long row_len,
+                                                           float* __restrict__ xb, long long* __restrict__ yb) {
+    const int r = blockIdx.y;
+    const long long src = perm[*step * eb + r];
+    const float* in = X + src * row_len;
+    float* out = xb + (long long)r * row_len;
+    if ((row_len & 3) == 0) {
+        const long long n4 = row_len >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+            reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(in)[i];
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row_len; i += (long long)gridDim.x * blockDim.x) out[i] = in[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) yb[r] = y[src];
+    __syncthreads();                                          // every thread of this CTA has read *step
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        if (atomicAdd(ticket, 1u) == total - 1) { *ticket = 0u; *step += 1; }      // last CTA: all others already consumed *step
+    }
+}
+
 }  // namespace mb
 
 using torch::Tensor;
@@ -308,4 +370,38 @@ std::vector<Tensor> evidential_loss_fwd_bwd(Tensor alpha, Tensor targets, double
             B, C, (float)lam, lam_t.has_value() ? lam_t->data_ptr<float>() : nullptr, loss.data_ptr<float>(), grad.data_ptr<float>());
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return {loss, grad};
+}
+
+// loss (0-dim), grad [B,C] (already divided by B).  `loss_acc` (optional 0-dim fp32) += loss inside the kernel.
+std::vector<Tensor> ce_loss_fwd_bwd(Tensor logits, Tensor targets, c10::optional<Tensor> loss_acc) {
+    c10::cuda::CUDAGuard guard(logits.device());
+    TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous() && logits.dtype() == torch::kFloat32 && targets.dtype() == torch::kInt64);
+    const int B = (int)logits.size(0), C = (int)logits.size(1);
+    TORCH_CHECK(B > 0 && targets.numel() == B);
+    Tensor loss = torch::empty({}, logits.options());
+    Tensor grad = torch::empty_like(logits);
+    mb::ce_loss_kernel<<<1, 256, 0, cur_stream()>>>(logits.data_ptr<float>(), reinterpret_cast<const long long*>(targets.data_ptr<int64_t>()), B, C,
+        loss.data_ptr<float>(), loss_acc.has_value() && loss_acc->defined() ? loss_acc->data_ptr<float>() : nullptr, grad.data_ptr<float>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return {loss, grad};
+}
+
+// xb [eb, *X.shape[1:]], yb [eb]; advances `step` (0-dim int64) by one; `ticket` is a zero-initialised int32 scratch word.
+std::vector<Tensor> gather_batch(Tensor X, Tensor y, Tensor perm, Tensor step, Tensor ticket, int64_t eb) {
+    c10::cuda::CUDAGuard guard(X.device());
+    TORCH_CHECK(X.is_contiguous() && X.dtype() == torch::kFloat32 && y.dtype() == torch::kInt64 && perm.dtype() == torch::kInt64 &&
+                step.dtype() == torch::kInt64 && ticket.dtype() == torch::kInt32 && eb > 0);
+    auto shape = X.sizes().vec();
+    shape[0] = eb;
+    Tensor xb = torch::empty(shape, X.options());
+    Tensor yb = torch::empty({eb}, y.options());
+    const int64_t row_len = X.numel() / std::max<int64_t>(1, X.size(0));
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, (row_len / 4 + 255) / 256));
+    dim3 grid(chunks, (unsigned)eb);
+    mb::gather_batch_kernel<<<grid, 256, 0, cur_stream()>>>(X.data_ptr<float>(), reinterpret_cast<const long long*>(y.data_ptr<int64_t>()),
+        reinterpret_cast<const long long*>(perm.data_ptr<int64_t>()), reinterpret_cast<long long*>(step.data_ptr<int64_t>()),
+        reinterpret_cast<unsigned int*>(ticket.data_ptr<int>()), (int)eb, (long long)row_len, xb.data_ptr<float>(),
+        reinterpret_cast<long long*>(yb.data_ptr<int64_t>()));
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return {xb, yb};
 }

@@ -81,6 +81,9 @@ class VirtualNode:
     params: List[nn.Parameter] = field(default_factory=list)
     perm_buf: Optional[torch.Tensor] = None
     step: Optional[torch.Tensor] = None
+    ticket: Optional[torch.Tensor] = None    # scratch word of gather_batch's last-CTA step increment
+    launches_per_step: int = 3               # our kernels per SGD step (measured when the step is traced / run eagerly)
+    autotuned: bool = False                  # first (serial, un-split) step done → cuDNN algorithm cache is warm
     arange: Optional[torch.Tensor] = None
     loss_sum: Optional[torch.Tensor] = None
     train_graph: Any = None
@@ -440,7 +443,17 @@ class B200Network:
         return x.permute(0, 3, 1, 2) if vn.nhwc else x        # zero-copy logical NCHW view of the NHWC shard
 
     def _split_backward(self, vn: VirtualNode):
-        if not self.opt.split_backward or self.opt.compute_dtype == "bf16":
+        mode = self.opt.split_backward
+        if mode == "auto":
+            # Measured on B200: with ≥ 4 nodes training concurrently on a GPU the extra side streams alias onto the same
+            # hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) and serialise (flagship 36 → 21 rounds/s); with 1–2 nodes per GPU the
+            # GPU is idle enough for the parallel branch to pay (ResNet-18 step 940 → 856 µs).
+            mode = self.V <= 2
+        if not mode or self.opt.compute_dtype == "bf16":
+            return None
+        if not vn.autotuned:
+            # The first step of every node runs stock single-stream autograd on an idle GPU: cudnn.benchmark times its candidate
+            # algorithms during that step, and timing them while a sibling kernel runs on the side stream picks bad ones.
             return None
         sb = getattr(vn, "split_bwd", None)
         if sb is None:
@@ -448,17 +461,41 @@ class B200Network:
             sb = vn.split_bwd = SplitBackward(self.device)
         return sb
 
+    def _plain_ce(self) -> bool:
+        c = self.criterion
+        return (not self.evidential) and (c is None or (type(c) is nn.CrossEntropyLoss and c.weight is None and c.reduction == "mean"
+                                                         and c.label_smoothing == 0.0 and c.ignore_index < 0))
+
+    def _backward(self, vn: VirtualNode, out: torch.Tensor, yb: torch.Tensor) -> bool:
+        """Loss + backward.  The two bundled losses are fused forward+backward kernels whose gradient seeds ``out.backward``
+        directly (no autograd nodes for the loss, no ones-like seed, no ``loss_sum`` add); anything else is stock autograd."""
+        from murmura_b200.models.mlp import EvidentialLoss
+        fp32 = out.dtype == torch.float32 and out.dim() == 2
+        if fp32 and self.evidential and isinstance(self.criterion, EvidentialLoss):
+            loss, grad = self.ext.evidential_loss_fwd_bwd(out.detach().contiguous(), yb, 0.0, self.lam_t)
+            out.backward(grad)
+            vn.loss_sum += loss
+            return True
+        if fp32 and self._plain_ce():
+            _, grad = self.ext.ce_loss_fwd_bwd(out.detach().contiguous(), yb, vn.loss_sum)
+            out.backward(grad)
+            return True
+        loss = self._loss(out, yb)
+        loss.backward()
+        vn.loss_sum += loss.detach()
+        return False
+
     def _train_step(self, vn: VirtualNode, lr: float) -> None:
-        pos = vn.step * vn.eb + vn.arange
-        idx = vn.perm_buf.index_select(0, pos)
-        xb = self._inputs(vn, vn.X.index_select(0, idx)); yb = vn.y.index_select(0, idx)
+        c0 = _ops.counters["launches"]
+        # one launch: rows perm[step·eb …] of the shard → (xb, yb); the device-side step counter advances inside the kernel
+        xb, yb = self.ext.gather_batch(vn.X, vn.y, vn.perm_buf, vn.step, vn.ticket, vn.eb)
+        xb = self._inputs(vn, xb)
         for p in vn.params:
             p.grad = None                                      # autograd hands us its own grad buffers: no accumulate pass
         sb = self._split_backward(vn)
         with self._autocast(), (sb if sb is not None else nullcontext()):
             out = vn.model(xb)
-        loss = self._loss(out, yb)
-        loss.backward()
+        fused_loss = self._backward(vn, out, yb)
         if sb is not None:
             grads = sb.join(vn.params)                         # weight gradients were computed on the side stream
         else:
@@ -469,8 +506,10 @@ class B200Network:
                     g = torch.empty_like(p).copy_(g)
                 grads.append(g)
         self.ext.sgd_multi(vn.params, grads, lr)              # one launch: θ -= lr·g for every tensor of the node
-        vn.step += 1
-        vn.loss_sum += loss.detach()
+        vn.launches_per_step = (_ops.counters["launches"] - c0) + 2 + (1 if fused_loss else 0)   # + gather_batch, sgd_multi, loss
+        if not vn.autotuned:
+            torch.cuda.synchronize(self.device)
+            vn.autotuned = True
 
     def _graphs_ok(self) -> bool:
         from murmura_b200.models.mlp import EvidentialLoss
@@ -487,6 +526,7 @@ class B200Network:
             if vn.perm_buf is None or vn.perm_buf.numel() != need:
                 vn.perm_buf = torch.zeros(need, dtype=torch.int64, device=self.device)
                 vn.step = torch.zeros((), dtype=torch.int64, device=self.device)
+                vn.ticket = torch.zeros((), dtype=torch.int32, device=self.device)
                 vn.arange = torch.arange(vn.eb, device=self.device)
                 vn.loss_sum = torch.zeros((), device=self.device)
                 vn.train_graph = None
@@ -500,6 +540,7 @@ class B200Network:
         vn.model.train()
         vn.perm_buf.copy_(torch.arange(vn.perm_buf.numel(), device=self.device) % vn.n)
         side = self.capture_streams[self.stream_of[vn.slot]]
+        torch.cuda.synchronize(self.device)                # idle GPU while cuDNN autotunes in the first warm-up step
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
@@ -553,7 +594,7 @@ class B200Network:
                 else:
                     for _ in range(epochs * vn.nb):
                         self._train_step(vn, lr)
-                self.kernel_launches += epochs * vn.nb * (2 if self._fused_evidential else 1)
+                self.kernel_launches += epochs * vn.nb * vn.launches_per_step
         self._join()
 
     # =========================================================================================

@@ -360,3 +360,18 @@ def test_split_backward_gradients_match_autograd_eager_and_graph():
         g.replay(); torch.cuda.synchronize()
         for gt, w in zip(static, want):
             assert float((gt - w).abs().max()) <= 2e-3 * (float(w.abs().max()) + 1e-6)
+
+
+@pytest.mark.parametrize("split", [True, False, "auto"])
+def test_training_with_split_backward_modes(split):
+    cfg = _cfg("fedavg", n=4, topo={"type": "ring", "num_nodes": 4}, rounds=3, b200={"split_backward": split},
+               data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 96, "partition_method": "iid"}})
+    net, _, _ = _build(cfg)
+    try:
+        hist = net.train(rounds=3, local_epochs=1, lr=0.05)
+        assert len(hist["round"]) == 3 and all(math.isfinite(a) for a in hist["mean_accuracy"])
+        assert hist["mean_accuracy"][-1] > 0.45
+        used = any(vn.split_bwd is not None for vn in net.nodes)
+        assert used == (split is True)                     # 4 nodes on one GPU: "auto" keeps the single-stream backward
+    finally:
+        net.close()

@@ -606,3 +606,35 @@ def test_bn_act_eval_and_fallbacks(ext):
     with torch.no_grad():
         assert torch.equal(ops.bn_act(xn, bn, relu=False), bn(xn))
     assert int(bn.num_batches_tracked) == 0
+
+
+@pytest.mark.parametrize("B,C", [(64, 10), (7, 62), (130, 6), (1, 3)])
+def test_ce_loss_fwd_bwd_matches_autograd(ext, B, C):
+    import torch.nn.functional as F
+    torch.manual_seed(B + C)
+    z = (torch.randn(B, C, device="cuda") * 3).requires_grad_(True)
+    t = torch.randint(0, C, (B,), device="cuda")
+    want = F.cross_entropy(z, t); want.backward()
+    acc = torch.full((), 2.5, device="cuda")
+    loss, grad = ext.ce_loss_fwd_bwd(z.detach(), t, acc)
+    assert abs(float(loss) - float(want)) < 1e-5 * max(1.0, abs(float(want)))
+    assert float((grad - z.grad).abs().max()) < 1e-6
+    assert abs(float(acc) - 2.5 - float(want)) < 1e-4
+    from murmura_b200 import ops
+    z2 = z.detach().clone().requires_grad_(True)
+    (ops.ce_loss(z2, t) * 3.0).backward()
+    assert float((z2.grad - 3.0 * z.grad).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(50, 32, 32, 3), (33, 561), (29, 7)])
+def test_gather_batch_walks_permutation_and_advances_step(ext, shape):
+    torch.manual_seed(1)
+    n, eb = shape[0], 8
+    X = torch.randn(*shape, device="cuda"); y = torch.randint(0, 9, (n,), device="cuda")
+    perm = torch.randperm(n, device="cuda")[: 3 * eb].contiguous()
+    step = torch.zeros((), dtype=torch.int64, device="cuda"); ticket = torch.zeros((), dtype=torch.int32, device="cuda")
+    for k in range(3):
+        xb, yb = ext.gather_batch(X, y, perm, step, ticket, eb)
+        idx = perm[k * eb:(k + 1) * eb]
+        assert torch.equal(xb, X.index_select(0, idx)) and torch.equal(yb, y.index_select(0, idx))
+        assert int(step) == k + 1 and int(ticket) == 0
