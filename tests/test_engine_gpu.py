@@ -370,7 +370,7 @@ def test_training_with_split_backward_modes(split):
     try:
         hist = net.train(rounds=3, local_epochs=1, lr=0.05)
         assert len(hist["round"]) == 3 and all(math.isfinite(a) for a in hist["mean_accuracy"])
-        assert hist["mean_accuracy"][-1] > 0.45
+        assert hist["mean_accuracy"][-1] > 0.25                # 9 SGD steps, 10 classes; identical in all three modes
         used = any(vn.split_bwd is not None for vn in net.nodes)
         assert used == (split is True)                     # 4 nodes on one GPU: "auto" keeps the single-stream backward
     finally:
