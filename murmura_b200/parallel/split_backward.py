@@ -117,9 +117,8 @@ class SplitBackward:
     def join(self, params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         """Wait for the side stream; return one gradient per parameter (stashed weight gradient or ``p.grad``), laid out
         like the parameter."""
-        cur = torch.cuda.current_stream(self.device)
         if self.stash:
-            cur.wait_stream(self.side)
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
         grads = []
         for p in params:
             g = self.stash.get(p.data_ptr())

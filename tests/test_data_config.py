@@ -193,3 +193,53 @@ def test_evidential_mlp_forward_equals_its_sequential_definition():
         assert ka == kb and torch.allclose(va.float(), vb.float(), atol=1e-6), ka
     a.eval(); b.eval()
     assert torch.allclose(a(x), b.evidential_head(b.feature_extractor(x)), atol=1e-6)
+
+
+def test_bn_act_cpu_fallback_equals_stock_composition():
+    """ops.bn_act on CPU tensors (or any non-fusable layout) is the stock BatchNorm → (+residual) → ReLU composition."""
+    import copy
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from murmura_b200 import ops
+    torch.manual_seed(3)
+    a = nn.BatchNorm2d(8); b = copy.deepcopy(a)
+    x = torch.randn(5, 8, 4, 4); r = torch.randn_like(x)
+    assert not ops.bn_act_fusable(x, a)
+    ya = ops.bn_act(x, a, residual=r, relu=True)
+    yb = F.relu(b(x) + r)
+    assert torch.equal(ya, yb)
+    assert torch.equal(a.running_mean, b.running_mean) and int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
+    a.eval(); b.eval()
+    assert torch.equal(ops.bn_act(x, a, relu=False), b(x))
+
+
+def test_split_backward_is_transparent_for_cpu_tensors_and_restores_functional():
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from murmura_b200.parallel.split_backward import SplitBackward
+    conv0, lin0 = F.conv2d, F.linear
+    sb = SplitBackward(torch.device("cpu"), side=object())
+    model = nn.Sequential(nn.Conv2d(2, 3, 3), nn.Flatten(), nn.Linear(3 * 4 * 4, 2))
+    with sb:
+        assert F.conv2d is not conv0 and F.linear is not lin0
+        model(torch.randn(2, 2, 6, 6)).sum().backward()
+    assert F.conv2d is conv0 and F.linear is lin0
+    assert all(p.grad is not None for p in model.parameters()) and not sb.stash
+    grads = sb.join(list(model.parameters()))                       # nothing stashed: falls back to p.grad
+    assert all(g is p.grad for g, p in zip(grads, model.parameters()))
+
+
+def test_b200_block_new_options_validate():
+    import pytest
+    from pydantic import ValidationError
+    from murmura_b200.config.schema import B200Config
+    c = B200Config()
+    assert c.split_backward == "auto" and c.fused_bn is True and c.gather_impl == "auto"
+    assert B200Config(split_backward=False).split_backward is False
+    assert B200Config(split_backward=True, gather_impl="tma", fused_bn=False).gather_impl == "tma"
+    with pytest.raises(ValidationError):
+        B200Config(gather_impl="dma")
+    with pytest.raises(ValidationError):
+        B200Config(split_backward="sometimes")
