@@ -58,9 +58,9 @@ class SplitBackward:
                     with torch.cuda.stream(owner.side):
                         _, gw, gb = _aten.convolution_backward(gy, x, w, ctx.bias_sizes, stride, padding, dilation, False, [0, 0],
                                                                groups, [False, True, ctx.bias_sizes is not None])
-                        owner.stash[ctx.keys[0]] = gw
+                        owner._put(ctx.keys[0], gw)
                         if ctx.bias_sizes is not None:
-                            owner.stash[ctx.keys[1]] = gb
+                            owner._put(ctx.keys[1], gb)
                     owner._keep.append((gy, x, w))
                 gx = None
                 if ctx.needs_input_grad[0]:
@@ -83,14 +83,19 @@ class SplitBackward:
                 gy2 = gy.reshape(-1, gy.shape[-1])
                 owner.side.wait_stream(cur)
                 with torch.cuda.stream(owner.side):
-                    owner.stash[ctx.keys[0]] = gy2.t().mm(x.reshape(-1, x.shape[-1]))
+                    owner._put(ctx.keys[0], gy2.t().mm(x.reshape(-1, x.shape[-1])))
                     if ctx.has_bias:
-                        owner.stash[ctx.keys[1]] = gy2.sum(0)
+                        owner._put(ctx.keys[1], gy2.sum(0))
                 owner._keep.append((gy, gy2, x))
                 gx = gy.matmul(w) if ctx.needs_input_grad[0] else None
                 return gx, None, None
 
         self._Conv2d, self._Linear = _Conv2d, _Linear
+
+    def _put(self, key: int, grad: torch.Tensor) -> None:
+        """Stash a weight gradient (called on the side stream); a parameter used by several layers accumulates."""
+        prev = self.stash.get(key)
+        self.stash[key] = grad if prev is None else prev + grad
 
     # ---- patched entry points -------------------------------------------------------------------------------------------
     def _conv2d(self, input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
