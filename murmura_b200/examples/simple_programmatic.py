@@ -21,15 +21,28 @@ class TinyNet(nn.Module):
         return self.body(x)
 
 
-def make_network(num_nodes: int = 10, samples: int = 100, seed: int = 0) -> Network:
+def create_simple_model() -> nn.Module:
+    """Same entry point name as the reference example (``simple_programmatic.py:15``): a fresh 10→50→2 MLP."""
+    return TinyNet()
+
+
+def create_synthetic_dataset(num_clients: int = 5, samples_per_client: int = 100, input_dim: int = 10, seed: int = 0):
+    """One linearly-separable ``TensorDataset`` per client (reference ``simple_programmatic.py:24`` builds random data the same
+    way); all clients share the separating direction so federation helps."""
     g = torch.Generator().manual_seed(seed)
-    w = torch.randn(10, generator=g)
+    w = torch.randn(input_dim, generator=g)
+    out = []
+    for _ in range(num_clients):
+        x = torch.randn(samples_per_client, input_dim, generator=g)
+        out.append(TensorDataset(x, (x @ w > 0).long()))
+    return out
+
+
+def make_network(num_nodes: int = 10, samples: int = 100, seed: int = 0) -> Network:
     nodes = []
-    for nid in range(num_nodes):
-        x = torch.randn(samples, 10, generator=g)
-        y = (x @ w > 0).long()
-        loader = DataLoader(TensorDataset(x, y), batch_size=32, shuffle=True)
-        nodes.append(Node(node_id=nid, model=TinyNet(), train_loader=loader, test_loader=loader,
+    for nid, ds in enumerate(create_synthetic_dataset(num_nodes, samples, 10, seed)):
+        loader = DataLoader(ds, batch_size=32, shuffle=True)
+        nodes.append(Node(node_id=nid, model=create_simple_model(), train_loader=loader, test_loader=loader,
                           aggregator=FedAvgAggregator(), device=torch.device("cpu")))
     return Network(nodes=nodes, topology=create_topology("ring", num_nodes=num_nodes))
 

@@ -243,3 +243,17 @@ def test_generate_figures(tmp_path):
     assert run.returncode == 0, run.stderr
     md = (tmp_path / "fig" / "summary.md").read_text()
     assert "uci_har__fedavg__none0__ring__a0.5" in md and "0.9000" in md and "bad" not in md
+
+
+def test_public_api_parity_with_reference_package():
+    """Every public name / method / parameter of the unmodified reference (baseline/_ref) exists in the same-named module here."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "murmura")):
+        import pytest
+        pytest.skip("reference install (baseline/_ref) not present")
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "api_parity.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "## Missing (0)" in out.stdout, out.stdout[-3000:]
