@@ -1,0 +1,193 @@
+"""Cross-implementation oracle: our CPU classes vs the UNMODIFIED reference package (baseline/_ref), same inputs → same outputs.
+
+Skipped when the reference install is absent.  Nothing here needs a GPU; the GPU suite then checks the kernels against *our*
+CPU classes, which closes the chain  reference ⇄ murmura_b200 (CPU) ⇄ sm_100a kernels.
+"""
+import copy
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+if not os.path.isdir(os.path.join(REF, "murmura")):
+    pytest.skip("reference install (baseline/_ref) not present", allow_module_level=True)
+if REF not in sys.path:
+    sys.path.insert(0, REF)
+
+import murmura as ref                                      # noqa: E402
+import murmura.aggregation as ref_agg                      # noqa: E402
+from murmura.attacks.directed import DirectedDeviationAttack as RefDirected      # noqa: E402
+from murmura.attacks.gaussian import GaussianAttack as RefGaussian               # noqa: E402
+from murmura.attacks.topology_liar import TopologyLiarAttack as RefLiar          # noqa: E402
+from murmura.data.partitioners import dirichlet_partition as ref_dirichlet, iid_partition as ref_iid   # noqa: E402
+from murmura.dmtt.state import DMTTNodeState as RefDMTT    # noqa: E402
+from murmura.topology.dynamic import MobilityModel as RefMobility                 # noqa: E402
+
+assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF)), "the name `murmura` must resolve to the reference install"
+
+import murmura_b200 as ours                                # noqa: E402
+import murmura_b200.aggregation as our_agg                 # noqa: E402
+from murmura_b200.attacks.directed import DirectedDeviationAttack               # noqa: E402
+from murmura_b200.attacks.gaussian import GaussianAttack                        # noqa: E402
+from murmura_b200.attacks.topology_liar import TopologyLiarAttack               # noqa: E402
+from murmura_b200.data.partitioners import dirichlet_partition, iid_partition  # noqa: E402
+from murmura_b200.dmtt.state import DMTTNodeState                               # noqa: E402
+from murmura_b200.topology.dynamic import MobilityModel                         # noqa: E402
+
+
+class _Net(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc1 = nn.Linear(12, 16); self.bn = nn.BatchNorm1d(16); self.fc2 = nn.Linear(16, 4)
+
+    def forward(self, x):
+        return self.fc2(torch.relu(self.bn(self.fc1(x))))
+
+
+def _states(n, seed, spread=0.3, outlier=None):
+    torch.manual_seed(seed)
+    base = _Net().state_dict()
+    out = []
+    for i in range(n):
+        st = {}
+        for k, v in base.items():
+            if v.dtype.is_floating_point:
+                scale = 25.0 if outlier == i else spread
+                st[k] = v.clone() + scale * torch.randn_like(v)
+            else:
+                st[k] = v.clone() + i
+        out.append(st)
+    return out
+
+
+def _same(a, b, atol=1e-6):
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k].dtype == b[k].dtype, k
+        assert torch.allclose(a[k].double(), b[k].double(), atol=atol, rtol=1e-6), k
+
+
+@pytest.mark.parametrize("topo,kw", [("ring", {}), ("fully", {}), ("erdos", {"p": 0.3, "seed": 7}), ("k-regular", {"k": 4}),
+                                     ("k-regular", {"k": 3}), ("er", {"p": 0.05, "seed": 1})])
+@pytest.mark.parametrize("n", [2, 5, 16])
+def test_topologies_identical(topo, kw, n, capsys):
+    a = ref.create_topology(topo, num_nodes=n, **kw)
+    b = ours.create_topology(topo, num_nodes=n, **kw)
+    assert [sorted(v) for v in a.neighbors] == [sorted(v) for v in b.neighbors]
+    assert a.num_nodes == b.num_nodes and a.is_connected() == b.is_connected() and abs(a.avg_degree() - b.avg_degree()) < 1e-12
+
+
+def test_attack_selection_and_payloads_identical(capsys):
+    for n, pct, seed in ((10, 0.3, 42), (7, 0.2, 3), (20, 0.05, 11)):
+        ra, oa = RefGaussian(n, pct, noise_std=2.0, seed=seed), GaussianAttack(n, pct, noise_std=2.0, seed=seed)
+        assert sorted(ra.get_compromised_nodes()) == sorted(oa.get_compromised_nodes())
+        rd, od = RefDirected(n, pct, lambda_param=-3.0, seed=seed), DirectedDeviationAttack(n, pct, lambda_param=-3.0, seed=seed)
+        assert sorted(rd.get_compromised_nodes()) == sorted(od.get_compromised_nodes())
+        rl, ol = RefLiar(n, pct, seed=seed), TopologyLiarAttack(n, pct, seed=seed)
+        assert sorted(rl.get_compromised_nodes()) == sorted(ol.get_compromised_nodes())
+        bad = sorted(rl.get_compromised_nodes())[0]
+        assert rl.get_false_claims(bad, [1, 2], 0) == ol.get_false_claims(bad, [1, 2], 0)
+        st = _states(1, seed)[0]
+        bad = sorted(rd.get_compromised_nodes())[0]
+        _same(rd.apply_attack(bad, copy.deepcopy(st), 0), od.apply_attack(bad, copy.deepcopy(st), 0))
+        torch.manual_seed(5); g1 = ra.apply_attack(bad, copy.deepcopy(st), 0)
+        torch.manual_seed(5); g2 = oa.apply_attack(bad, copy.deepcopy(st), 0)
+        _same(g1, g2)
+        honest = next(i for i in range(n) if i not in ra.get_compromised_nodes())
+        _same(ra.apply_attack(honest, copy.deepcopy(st), 0), oa.apply_attack(honest, copy.deepcopy(st), 0))
+
+
+def test_partitioners_identical():
+    labels = np.random.RandomState(0).randint(0, 10, size=3000)
+    for alpha, clients in ((0.1, 10), (0.5, 8), (5.0, 20)):
+        a = ref_dirichlet(labels, clients, alpha=alpha, min_samples_per_client=5, seed=11)
+        b = dirichlet_partition(labels, clients, alpha=alpha, min_samples_per_client=5, seed=11)
+        assert [sorted(map(int, x)) for x in a] == [sorted(map(int, x)) for x in b]
+    a, b = ref_iid(1000, 7, seed=3), iid_partition(1000, 7, seed=3)
+    assert [list(map(int, x)) for x in a] == [list(map(int, x)) for x in b]
+
+
+def test_mobility_model_identical():
+    kw = dict(num_nodes=24, area_size=100.0, comm_range=28.0, max_speed=6.0, seed=9)
+    a, b = RefMobility(**kw), MobilityModel(**kw)
+    for r in (0, 1, 5, 3, 17):
+        assert {i: sorted(v) for i, v in a.neighbors_at(r).items()} == {i: sorted(v) for i, v in b.neighbors_at(r).items()}
+        assert abs(a.torus_dist(2, 7, r) - b.torus_dist(2, 7, r)) < 1e-12
+
+
+def test_dmtt_state_identical():
+    from murmura.config.schema import DMTTConfig as RefCfg
+    from murmura_b200.config.schema import DMTTConfig
+    a, b = RefDMTT(0, RefCfg()), DMTTNodeState(0, DMTTConfig())
+    rng = random.Random(4)
+    for step in range(40):
+        j = rng.randrange(1, 9)
+        ack = rng.random() < 0.7
+        d, x = rng.randrange(0, 5), rng.randrange(0, 3)
+        acc, vac = rng.random(), rng.random()
+        for s in (a, b):
+            s.update_link_reliability(j, ack)
+            s.update_trust(j, d, x)
+        assert abs(a.topo_trust(j) - b.topo_trust(j)) < 1e-12
+        assert abs(a.model_score(acc, vac) - b.model_score(acc, vac)) < 1e-12
+        assert abs(a.collab_score(j, a.model_score(acc, vac)) - b.collab_score(j, b.model_score(acc, vac))) < 1e-12
+    scores = {j: rng.random() for j in range(1, 7)}
+    assert a.top_b(list(range(1, 9)), scores, 3) == b.top_b(list(range(1, 9)), scores, 3)
+
+
+AGGS = [("FedAvgAggregator", {}), ("KrumAggregator", {"num_compromised": 1}), ("KrumAggregator", {"num_compromised": 0}),
+        ("BALANCEAggregator", {"gamma": 1.0, "kappa": 1.0, "alpha": 0.5, "total_rounds": 10}),
+        ("BALANCEAggregator", {"gamma": 0.05, "min_neighbors": 2, "total_rounds": 10}),
+        ("UBARAggregator", {"rho": 0.5, "alpha": 0.4}),
+        ("SketchguardAggregator", {"sketch_size": 64, "gamma": 1.5, "total_rounds": 10}),
+        ("SketchguardAggregator", {"sketch_size": 32, "gamma": 0.01, "min_neighbors": 2, "total_rounds": 10})]
+
+
+@pytest.mark.parametrize("name,params", AGGS)
+def test_aggregators_identical(name, params):
+    model = _Net()
+    dim = sum(v.numel() for v in model.state_dict().values() if v.dtype.is_floating_point)
+    if name == "SketchguardAggregator":
+        params = dict(params, model_dim=dim)
+    ra, oa = getattr(ref_agg, name)(**params), getattr(our_agg, name)(**params)
+    for rnd, (seed, outlier) in enumerate(((1, None), (2, 2), (3, 0), (4, None))):
+        sts = _states(6, seed, outlier=outlier)
+        own, nbrs = sts[0], {i: sts[i] for i in range(1, 6)}
+        r = ra.aggregate(0, copy.deepcopy(own), copy.deepcopy(nbrs), rnd)
+        o = oa.aggregate(0, copy.deepcopy(own), copy.deepcopy(nbrs), rnd)
+        _same(r, o, atol=1e-5)
+
+
+def test_loss_filtered_aggregators_identical():
+    """UBAR stage 2 and EvidentialTrust evaluate neighbours on local data: same loader, same template → same result."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from murmura.examples.wearables.models import EvidentialHARClassifier as RefHAR
+    from murmura_b200.models.mlp import EvidentialHARClassifier
+    torch.manual_seed(0)
+    x = torch.randn(128, 24); y = torch.randint(0, 5, (128,))
+    loader = DataLoader(TensorDataset(x, y), batch_size=32, shuffle=False)
+    kw = dict(input_dim=24, hidden_dims=[16, 8], num_classes=5, dropout=0.0)
+    tmpl_r, tmpl_o = RefHAR(**kw), EvidentialHARClassifier(**kw)
+    tmpl_o.load_state_dict(tmpl_r.state_dict())
+    assert list(tmpl_r.state_dict()) == list(tmpl_o.state_dict())
+    base = tmpl_r.state_dict()
+    sts = []
+    for i in range(5):
+        torch.manual_seed(10 + i)
+        sts.append({k: (v + (0.05 + 0.3 * (i == 3)) * torch.randn_like(v)) if v.dtype.is_floating_point else v.clone() for k, v in base.items()})
+    for name, params in (("UBARAggregator", {"rho": 0.6, "alpha": 0.5}),
+                         ("EvidentialTrustAggregator", {"trust_threshold": 0.1, "self_weight": 0.5, "max_eval_samples": 64})):
+        ra, oa = getattr(ref_agg, name)(**params), getattr(our_agg, name)(**params)
+        for rnd in range(3):
+            mr, mo = copy.deepcopy(tmpl_r).eval(), copy.deepcopy(tmpl_o).eval()
+            r = ra.aggregate(0, copy.deepcopy(sts[0]), {i: copy.deepcopy(sts[i]) for i in range(1, 5)}, rnd,
+                             train_loader=loader, model_template=mr, device=torch.device("cpu"))
+            o = oa.aggregate(0, copy.deepcopy(sts[0]), {i: copy.deepcopy(sts[i]) for i in range(1, 5)}, rnd,
+                             train_loader=loader, model_template=mo, device=torch.device("cpu"))
+            _same(r, o, atol=1e-5)
