@@ -199,9 +199,13 @@ def test_experiment_harness(tmp_path):
     env = dict(os.environ, PYTHONPATH=ROOT)
     gen = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "generate_configs.py"), "--out", str(tmp_path / "cfgs"),
                           "--backend", "simulation", "--rounds", "2"], capture_output=True, text=True, env=env)
-    assert gen.returncode == 0 and "wrote" in gen.stdout
-    files = sorted(os.listdir(tmp_path / "cfgs"))
-    assert len(files) > 100 and all(load_config(tmp_path / "cfgs" / f) for f in files[:5])
+    assert gen.returncode == 0 and "wrote" in gen.stdout and "covering 314 experiment slots" in gen.stdout
+    files = sorted(f for f in os.listdir(tmp_path / "cfgs") if f.endswith(".yaml"))
+    assert len(files) > 250 and all(load_config(tmp_path / "cfgs" / f) for f in files)
+    index = json.load(open(tmp_path / "cfgs" / "index.json"))
+    assert {k: len(v) for k, v in index.items()} == {"baseline": 18, "heterogeneity": 54, "attacks": 108, "topologies": 48,
+                                                      "ablation": 51, "dmtt": 3, "scenarios": 32}
+    assert all(f in files for fam in index.values() for f in fam.values())
     one = tmp_path / "one"; one.mkdir()
     (one / "a.yaml").write_text((tmp_path / "cfgs" / "ppg_dalia__fedavg__none0__ring__a0.5.yaml").read_text())
     res = tmp_path / "res.json"
@@ -242,6 +246,13 @@ def test_generate_figures(tmp_path):
                          capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT))
     assert run.returncode == 0, run.stderr
     md = (tmp_path / "fig" / "summary.md").read_text()
+    (tmp_path / "index.json").write_text(json.dumps({"topologies": {"uci_har/fedavg_ring": "uci_har__fedavg__none0__ring__a0.5.yaml",
+                                                                     "uci_har/fedavg_fully": "missing.yaml"}}))
+    run2 = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "generate_figures.py"), str(tmp_path / "r.json"), "--out", str(tmp_path / "fig"),
+                           "--index", str(tmp_path / "index.json")], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert run2.returncode == 0, run2.stderr
+    fam = (tmp_path / "fig" / "families.md").read_text()
+    assert "## topologies (2 experiments)" in fam and "0.9000 ± 0.0100" in fam and "1/2 done" in fam
     assert "uci_har__fedavg__none0__ring__a0.5" in md and "0.9000" in md and "bad" not in md
 
 
