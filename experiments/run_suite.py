@@ -52,9 +52,18 @@ def main():
     ap.add_argument("config_dir"); ap.add_argument("--results", default="experiments/results.json")
     ap.add_argument("--device", default=None); ap.add_argument("--timeout", type=int, default=1800)
     ap.add_argument("--limit", type=int, default=0)
+    ap.add_argument("--families", nargs="*", default=None,
+                    help="run only these experiment families (keys of <config_dir>/index.json written by generate_configs.py)")
     args = ap.parse_args()
     results = json.load(open(args.results)) if os.path.exists(args.results) else {}
     todo = sorted(glob.glob(os.path.join(args.config_dir, "*.yaml")))
+    if args.families:
+        index = json.load(open(os.path.join(args.config_dir, "index.json")))
+        unknown = [f for f in args.families if f not in index]
+        if unknown:
+            raise SystemExit(f"unknown families {unknown}; available: {sorted(index)}")
+        keep = {name for f in args.families for name in index[f].values()}
+        todo = [p for p in todo if os.path.basename(p) in keep]
     done = 0
     for path in todo:
         key = os.path.splitext(os.path.basename(path))[0]
