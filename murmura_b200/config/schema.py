@@ -121,6 +121,8 @@ class B200Config(BaseModel):
         default="balanced", description="virtual-node → GPU map: balanced = longest-shard-first onto the least-loaded GPU")
     unroll_round: bool = Field(default=True, description="capture ALL local steps of a node's round (epochs x batches) in one CUDA "
                                "graph instead of one graph per step (fewer graph launches; matters for tiny models)")
+    batched_mlp_train: bool = Field(default=False, description="train all MLP-family nodes of a GPU in one batched step (strided-batched GEMMs "
+                                    "over arena-row views, masked per-node BatchNorm/SGD); opt-in, falls back to per-node graphs")
     grouped_mlp: bool = Field(default=True, description="score foreign MLP weights (UBAR stage 2 / EvidentialTrust / DMTT) with the "
                               "grouped tcgen05 forward (TF32) instead of per-candidate graph replays (fp32)")
     streams: int = Field(default=0, description="concurrent CUDA streams for virtual-node training (0 = auto: min(16, nodes on this GPU))")

@@ -572,6 +572,8 @@ class B200Network:
         self._fused_evidential = self.evidential and isinstance(self.criterion, EvidentialLoss)
         if isinstance(self.criterion, EvidentialLoss):
             self.lam_t.fill_(self.criterion.anneal(self.round_idx))
+        if self.opt.batched_mlp_train and self._batched_training(epochs, lr):
+            return
         self._fork()
         for i in self.launch_order:
             vn = self.nodes[i]
@@ -596,6 +598,91 @@ class B200Network:
                         self._train_step(vn, lr)
                 self.kernel_launches += epochs * vn.nb * vn.launches_per_step
         self._join()
+
+    # ---- K8b: all MLP nodes of this GPU in one batched step (opt-in: b200.batched_mlp_train) ------------------------------
+    def _batched_setup(self, epochs: int, lr: float):
+        """Build the batched trainer + the CUDA graph of a whole round; returns None when this GPU's nodes do not qualify."""
+        from murmura_b200.models.mlp import MLP, EvidentialLoss, EvidentialMLP
+        from murmura_b200.parallel.batched_mlp import BatchedMLPTrainer
+        live = [vn for vn in self.nodes if not vn.byzantine and vn.nb > 0]
+        if (self.V < 2 or not live or not isinstance(self.nodes[0].model, (MLP, EvidentialMLP)) or self._host_shards
+                or len({vn.eb for vn in live}) != 1 or self.opt.compute_dtype == "bf16"):
+            return None
+        if self.evidential != isinstance(self.nodes[0].model, EvidentialMLP):
+            return None
+        if self.evidential and not isinstance(self.criterion, EvidentialLoss):
+            return None
+        if not self.evidential and not self._plain_ce():
+            return None
+        eb = live[0].eb
+        steps = max(vn.nb for vn in live) * epochs
+        n_max = max(max(vn.n for vn in self.nodes), 1)
+        st: Dict[str, Any] = {"eb": eb, "steps": steps}
+        st["xpad"] = torch.zeros(self.V, n_max, *self.nodes[0].X.shape[1:], device=self.device)
+        st["ypad"] = torch.zeros(self.V, n_max, dtype=torch.long, device=self.device)
+        for vi, vn in enumerate(self.nodes):
+            st["xpad"][vi, :vn.n].copy_(vn.X); st["ypad"][vi, :vn.n].copy_(vn.y)
+        act = torch.zeros(steps, self.V, device=self.device)
+        for vi, vn in enumerate(self.nodes):
+            if not vn.byzantine and vn.nb > 0:
+                act[: vn.nb * epochs, vi] = 1.0
+        st["act"] = act
+        st["perm"] = torch.zeros(self.V, steps * eb, dtype=torch.long, device=self.device)
+        st["trainer"] = trainer = BatchedMLPTrainer(self.nodes[0].model, self.layout, self.live[: self.V], self.ints[: self.V] if self.layout.Pi else None)
+        lam = self.lam_t if self.evidential else 0.0
+
+        def body():
+            for t in range(steps):
+                xb, yb = trainer.gather(st["xpad"], st["ypad"], st["perm"][:, t * eb:(t + 1) * eb])
+                trainer.step(xb, yb, act[t], lr, lam)
+
+        st["body"] = body
+        st["graph"] = None
+        if self._graphs_ok():
+            snap, snap_i = self.live.clone(), self.ints.clone()
+            rng = torch.cuda.get_rng_state(self.device)
+            side = self.capture_streams[0]
+            torch.cuda.synchronize(self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                body()
+            st["graph"] = graph
+            self.live.copy_(snap); self.ints.copy_(snap_i)
+            torch.cuda.set_rng_state(rng, self.device)
+        return st
+
+    def _batched_training(self, epochs: int, lr: float) -> bool:
+        key = (epochs, lr)
+        cache = self.__dict__.setdefault("_batched_cache", {})
+        if key not in cache:
+            try:
+                cache[key] = self._batched_setup(epochs, lr)
+            except Exception as exc:  # noqa: BLE001 - opt-in fast path: report and use the per-node graphs
+                if self.is_primary:
+                    print(f"[b200] batched MLP training unavailable ({type(exc).__name__}: {exc}); using per-node graphs")
+                cache[key] = None
+        st = cache[key]
+        if st is None:
+            return False
+        eb = st["eb"]
+        for vi, vn in enumerate(self.nodes):                       # fresh shuffles: epochs × nb batches of every node
+            if vn.byzantine or vn.nb == 0:
+                continue
+            take = vn.nb * eb
+            keys = torch.rand(epochs, vn.n, device=self.device)
+            st["perm"][vi, : epochs * take].copy_(keys.argsort(dim=1)[:, :take].reshape(-1))
+        for vn in self.nodes:
+            vn.model.train()
+        if st["graph"] is not None:
+            st["graph"].replay()
+        else:
+            st["body"]()
+        self.kernel_launches += st["steps"]
+        return True
 
     # =========================================================================================
     # publish + aggregation plans

@@ -243,3 +243,54 @@ def test_b200_block_new_options_validate():
         B200Config(gather_impl="dma")
     with pytest.raises(ValidationError):
         B200Config(split_backward="sometimes")
+
+
+@pytest.mark.parametrize("family", ["evidential", "plain"])
+def test_batched_mlp_trainer_equals_per_node_sgd(family):
+    """K8b: one batched step over arena-row views == every node's own forward/backward/SGD step (incl. BatchNorm running
+    statistics, num_batches_tracked and nodes that sit a step out)."""
+    import copy
+    import torch
+    import torch.nn.functional as F
+    from murmura_b200.models.mlp import MLP, EvidentialHARClassifier, evidential_loss_reference
+    from murmura_b200.parallel.arena import StateLayout
+    from murmura_b200.parallel.batched_mlp import BatchedMLPTrainer
+    torch.manual_seed(0)
+    V, B, Fin, C, lr, lam = 4, 16, 20, 5, 0.05, 0.3
+    make = (lambda: EvidentialHARClassifier(input_dim=Fin, hidden_dims=(12, 8), num_classes=C, dropout=0.0)) if family == "evidential" \
+        else (lambda: MLP(input_dim=Fin, hidden_dims=(12,), num_classes=C))
+    models = [make() for _ in range(V)]
+    layout = StateLayout.from_model(models[0])
+    rows = torch.zeros(V, layout.stride)
+    ints = torch.zeros(V, max(layout.Pi, 1), dtype=torch.int64)
+    for v, m in enumerate(models):                                    # flatten every node's state into its arena row
+        sd = m.state_dict()
+        for e in layout.float_entries():
+            rows[v, e.offset:e.offset + e.numel] = sd[e.name].reshape(-1)
+        for e in layout.int_entries():
+            ints[v, e.offset:e.offset + e.numel] = sd[e.name].reshape(-1)
+    trainer = BatchedMLPTrainer(models[0], layout, rows, ints if layout.Pi else None)
+    refs = [copy.deepcopy(m).train() for m in models]
+    for step in range(4):
+        x = torch.randn(V, B, Fin); y = torch.randint(0, C, (V, B))
+        active = torch.tensor([1.0, 1.0, 0.0 if step >= 2 else 1.0, 1.0 if step != 1 else 0.0])
+        trainer.step(x, y, active, lr, lam)
+        for v, m in enumerate(refs):
+            if active[v] == 0:
+                continue
+            for p in m.parameters():
+                p.grad = None
+            out = m(x[v])
+            loss = evidential_loss_reference(out, y[v], lam) if family == "evidential" else F.cross_entropy(out, y[v])
+            loss.backward()
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.add_(p.grad, alpha=-lr)
+    for v, m in enumerate(refs):
+        got = layout.row_views(rows[v], ints[v] if layout.Pi else None)
+        for k, want in m.state_dict().items():
+            assert torch.allclose(got[k].double(), want.double(), atol=2e-5, rtol=1e-4), (v, k)
+    xp, yp = torch.randn(V, 9, Fin), torch.randint(0, C, (V, 9))
+    idx = torch.randint(0, 9, (V, 3))
+    gx, gy = BatchedMLPTrainer.gather(xp, yp, idx)
+    assert all(torch.equal(gx[v], xp[v][idx[v]]) and torch.equal(gy[v], yp[v][idx[v]]) for v in range(V))
