@@ -45,3 +45,9 @@ class SyntheticRefAdapter:
 def resnet18(num_classes: int = 10):
     import torchvision
     return torchvision.models.resnet18(num_classes=num_classes)
+
+
+def mlp(input_dim: int = 784, hidden: int = 200, num_classes: int = 10):
+    """Stock 2-layer MLP for BASELINE config 1 (plain torch.nn, nothing from this repo)."""
+    import torch.nn as nn
+    return nn.Sequential(nn.Flatten(), nn.Linear(input_dim, hidden), nn.ReLU(), nn.Linear(hidden, num_classes))
