@@ -17,7 +17,9 @@ from typing import Any, Callable, Dict, List, Optional
 import numpy as np
 import torch
 import torch.nn as nn
-from torch.utils.data import DataLoader
+from torch.utils.data import DataLoader  # noqa: F401  (re-exported for user code that builds Nodes by hand)
+
+from murmura_b200.data.fast_loader import make_loaders
 
 from murmura_b200.attacks.base import Attack
 from murmura_b200.core.node import Node
@@ -139,12 +141,9 @@ class Network:
         attack = build_attack(config)
         nodes: List[Node] = []
         for nid in range(config.topology.num_nodes):
-            shard = dataset_adapter.get_client_data(nid)
-            n = len(shard)
-            bs = min(config.training.batch_size, max(2, n))
+            train_loader, test_loader, _ = make_loaders(dataset_adapter, nid, config.training.batch_size)
             nodes.append(Node(
-                node_id=nid, model=model_factory(),
-                train_loader=DataLoader(shard, batch_size=bs, shuffle=True, drop_last=n > bs),
-                test_loader=DataLoader(shard, batch_size=bs, shuffle=False),   # evaluates on the training shard
+                node_id=nid, model=model_factory(), train_loader=train_loader,
+                test_loader=test_loader,                                       # evaluates on the training shard
                 aggregator=aggregator_factory(nid), device=device, criterion=criterion, evidential=evidential))
         return cls(nodes=nodes, topology=topology, attack=attack)

@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Set
 
 import torch
 import zmq
-from torch.utils.data import DataLoader
+from murmura_b200.data.fast_loader import make_loaders
 
 from murmura_b200.config.loader import load_config
 from murmura_b200.config.schema import Config
@@ -183,11 +183,7 @@ class NodeProcess:
         model_factory = build_model_factory(cfg)
         aggregator_factory = build_aggregator_factory(cfg, model_factory, device)
         criterion, evidential = build_criterion(cfg)
-        shard = adapter.get_client_data(self.node_id)
-        n = len(shard)
-        bs = min(cfg.training.batch_size, max(2, n))
-        return Node(node_id=self.node_id, model=model_factory().to(device),
-                    train_loader=DataLoader(shard, batch_size=bs, shuffle=True, drop_last=n > bs),
-                    test_loader=DataLoader(shard, batch_size=bs, shuffle=False),
+        train_loader, test_loader, _ = make_loaders(adapter, self.node_id, cfg.training.batch_size)
+        return Node(node_id=self.node_id, model=model_factory().to(device), train_loader=train_loader, test_loader=test_loader,
                     aggregator=aggregator_factory(self.node_id), device=device, criterion=criterion,
                     evidential=evidential)

@@ -294,3 +294,25 @@ def test_batched_mlp_trainer_equals_per_node_sgd(family):
     idx = torch.randint(0, 9, (V, 3))
     gx, gy = BatchedMLPTrainer.gather(xp, yp, idx)
     assert all(torch.equal(gx[v], xp[v][idx[v]]) and torch.equal(gy[v], yp[v][idx[v]]) for v in range(V))
+
+
+@pytest.mark.parametrize("n,bs,shuffle,drop_last", [(100, 32, True, True), (100, 32, False, False), (64, 64, True, False), (5, 2, True, True)])
+def test_fast_tensor_loader_is_bit_identical_to_dataloader(n, bs, shuffle, drop_last):
+    """Same batches AND same global-RNG consumption as the stock DataLoader, for several epochs in a row."""
+    import torch
+    from torch.utils.data import DataLoader, TensorDataset
+    from murmura_b200.data.fast_loader import FastTensorLoader
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, 7, generator=g); y = torch.randint(0, 5, (n,), generator=g)
+    ref = DataLoader(TensorDataset(x, y), batch_size=bs, shuffle=shuffle, drop_last=drop_last)
+    fast = FastTensorLoader(x, y, bs, shuffle=shuffle, drop_last=drop_last)
+    assert len(ref) == len(fast)
+    torch.manual_seed(123); a = [[(xb.clone(), yb.clone()) for xb, yb in ref] for _ in range(3)]; ra = torch.rand(3)
+    torch.manual_seed(123); b = [[(xb.clone(), yb.clone()) for xb, yb in fast] for _ in range(3)]; rb = torch.rand(3)
+    assert torch.equal(ra, rb)                                          # the global generator is in the same state afterwards
+    for ea, eb in zip(a, b):
+        assert len(ea) == len(eb)
+        for (xa, ya), (xb_, yb_) in zip(ea, eb):
+            assert torch.equal(xa, xb_) and torch.equal(ya, yb_) and ya.dtype == yb_.dtype
+    torch.manual_seed(9); first_ref = next(iter(ref)); torch.manual_seed(9); first_fast = next(iter(fast))       # UBAR's next(iter(loader))
+    assert torch.equal(first_ref[0], first_fast[0])
