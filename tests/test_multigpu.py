@@ -1,5 +1,5 @@
-"""Multi-GPU fused exchange+aggregate (needs >= 2 GPUs; skipped otherwise).  Also a 1-rank run of the same script
-so the single-GPU tier still exercises the SPMD code path under torchrun."""
+"""Multi-GPU fused exchange+aggregate: `scripts/mp_check.py` under torchrun on 2 GPUs and on every GPU of the box
+(skipped when the box has fewer; the single-GPU tier covers the same kernels through `test_engine_gpu.py`)."""
 import os
 import subprocess
 import sys
