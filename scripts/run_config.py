@@ -3,7 +3,7 @@
     python scripts/run_config.py CONFIG.yaml [--rounds K] [--warmup W] [--transport p2p|nccl] [--set b200.key=value ...]
     (multi-GPU: python -m torch.distributed.run --nproc-per-node N scripts/run_config.py …)
 """
-import argparse, json, os, sys, time
+import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from murmura_b200 import Network

@@ -3,7 +3,6 @@ import json
 import numpy as np
 import pytest
 import torch
-import yaml
 from pydantic import ValidationError
 
 from murmura_b200.config import Config, load_config, save_config

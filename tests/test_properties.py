@@ -1,8 +1,6 @@
 """Property tests (hypothesis) for the pure-function layer: topologies, partitioners, aggregators, layout, placement."""
-import math
 
 import numpy as np
-import pytest
 import torch
 from hypothesis import given, settings, strategies as st
 

@@ -8,7 +8,6 @@ file of the suite on purpose.
 import math
 
 import pytest
-import torch
 
 pytestmark = pytest.mark.gpu
 
