@@ -1,11 +1,12 @@
 """Byzantine-robust aggregation rules (CPU oracles + device kernel plans)."""
-from murmura_b200.aggregation.base import Aggregator
-from murmura_b200.aggregation.fedavg import FedAvgAggregator
-from murmura_b200.aggregation.krum import KrumAggregator
-from murmura_b200.aggregation.balance import BALANCEAggregator
-from murmura_b200.aggregation.sketchguard import SketchguardAggregator
-from murmura_b200.aggregation.ubar import UBARAggregator
-from murmura_b200.aggregation.evidential_trust import EvidentialTrustAggregator
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["Aggregator", "FedAvgAggregator", "KrumAggregator", "BALANCEAggregator",
-           "SketchguardAggregator", "UBARAggregator", "EvidentialTrustAggregator"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "base": ["Aggregator"],
+    "fedavg": ["FedAvgAggregator"],
+    "krum": ["KrumAggregator"],
+    "balance": ["BALANCEAggregator"],
+    "sketchguard": ["SketchguardAggregator"],
+    "ubar": ["UBARAggregator"],
+    "evidential_trust": ["EvidentialTrustAggregator"],
+})

@@ -1,7 +1,9 @@
 """Byzantine attack injectors."""
-from murmura_b200.attacks.base import Attack
-from murmura_b200.attacks.gaussian import GaussianAttack
-from murmura_b200.attacks.directed import DirectedDeviationAttack
-from murmura_b200.attacks.topology_liar import TopologyLiarAttack
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["Attack", "GaussianAttack", "DirectedDeviationAttack", "TopologyLiarAttack"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "base": ["Attack"],
+    "gaussian": ["GaussianAttack"],
+    "directed": ["DirectedDeviationAttack"],
+    "topology_liar": ["TopologyLiarAttack"],
+})

@@ -1,9 +1,7 @@
 """Experiment configuration (schema + loader)."""
-from murmura_b200.config.schema import (Config, ExperimentConfig, TopologyConfig, AggregationConfig,
-                                        AttackConfig, TrainingConfig, DataConfig, ModelConfig,
-                                        DistributedConfig, MobilityConfig, DMTTConfig, B200Config)
-from murmura_b200.config.loader import load_config, save_config
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["Config", "ExperimentConfig", "TopologyConfig", "AggregationConfig", "AttackConfig",
-           "TrainingConfig", "DataConfig", "ModelConfig", "DistributedConfig", "MobilityConfig",
-           "DMTTConfig", "B200Config", "load_config", "save_config"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "schema": ["Config", "ExperimentConfig", "TopologyConfig", "AggregationConfig", "AttackConfig", "TrainingConfig", "DataConfig", "ModelConfig", "DistributedConfig", "MobilityConfig", "DMTTConfig", "B200Config"],
+    "loader": ["load_config", "save_config"],
+})

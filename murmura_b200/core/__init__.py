@@ -1,6 +1,8 @@
 """Core runtime: Node, Network and type aliases."""
-from murmura_b200.core.types import ModelState, DataPartition, ModelProtocol
-from murmura_b200.core.node import Node
-from murmura_b200.core.network import Network
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["Network", "Node", "ModelState", "DataPartition", "ModelProtocol"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "types": ["ModelState", "DataPartition", "ModelProtocol"],
+    "node": ["Node"],
+    "network": ["Network"],
+})

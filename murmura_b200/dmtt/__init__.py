@@ -1,5 +1,7 @@
 """DMTT — dynamic topology with trusted collaborator selection."""
-from murmura_b200.dmtt.state import DMTTNodeState
-from murmura_b200.dmtt.node_process import DMTTNodeProcess
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["DMTTNodeState", "DMTTNodeProcess"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "state": ["DMTTNodeState"],
+    "node_process": ["DMTTNodeProcess"],
+})

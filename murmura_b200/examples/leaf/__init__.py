@@ -1,5 +1,7 @@
 """LEAF benchmark integration (FEMNIST, CelebA)."""
-from murmura_b200.examples.leaf.adapter import load_leaf_adapter
-from murmura_b200.examples.leaf.model_factories import get_leaf_model_factory
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["load_leaf_adapter", "get_leaf_model_factory"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "adapter": ["load_leaf_adapter"],
+    "model_factories": ["get_leaf_model_factory"],
+})

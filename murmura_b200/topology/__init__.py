@@ -1,6 +1,8 @@
 """Network topologies (static generators + mobility-driven G^t)."""
-from murmura_b200.topology.base import Topology
-from murmura_b200.topology.generators import create_topology
-from murmura_b200.topology.dynamic import MobilityModel
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["Topology", "create_topology", "MobilityModel"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "base": ["Topology"],
+    "generators": ["create_topology"],
+    "dynamic": ["MobilityModel"],
+})

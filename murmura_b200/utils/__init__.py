@@ -1,6 +1,8 @@
-"""Utilities (device, seeding, metrics).  ``factories`` is imported lazily by callers."""
-from murmura_b200.utils.device import get_device
-from murmura_b200.utils.seed import set_seed
-from murmura_b200.utils.metrics import evaluate_model, compute_accuracy
+"""Utilities (device, seeding, metrics, factories)."""
+from murmura_b200._lazy import lazy_exports
 
-__all__ = ["get_device", "set_seed", "evaluate_model", "compute_accuracy"]
+__getattr__, __dir__, __all__ = lazy_exports(__name__, {
+    "device": ["get_device"],
+    "seed": ["set_seed"],
+    "metrics": ["evaluate_model", "compute_accuracy"],
+})
