@@ -16,17 +16,68 @@ from typing import Dict, List, Optional, Set
 
 import torch
 import zmq
-from murmura_b200.data.fast_loader import make_loaders
 
 from murmura_b200.config.loader import load_config
 from murmura_b200.config.schema import Config
 from murmura_b200.core.node import Node
 from murmura_b200.core.types import ModelState
+from murmura_b200.data.fast_loader import make_loaders
 from murmura_b200.distributed.endpoints import Endpoints
 from murmura_b200.distributed.messaging import MsgType, decode_full, encode, pack_obj, pack_state, unpack_state
 from murmura_b200.utils.factories import (build_aggregator_factory, build_attack, build_criterion,
                                           build_dataset_adapter, build_mobility_model, build_model_factory)
 from murmura_b200.utils.seed import set_seed
+
+
+class Mailbox:
+    """The ZeroMQ side of one node: a bound PULL inbox, PUSH outboxes connected on first use, and the uplink to the monitor.
+    Frames are the multipart messages of :mod:`murmura_b200.distributed.messaging`."""
+
+    def __init__(self, node_id: int, endpoints: Endpoints):
+        self.node_id, self.endpoints = node_id, endpoints
+        self.ctx: Optional[zmq.Context] = None
+        self.inbox = None
+        self.uplink = None
+        self.outboxes: Dict[int, zmq.Socket] = {}
+
+    def open(self, peers) -> "Mailbox":
+        self.ctx = zmq.Context()
+        self.inbox = self.ctx.socket(zmq.PULL)
+        self.inbox.bind(self.endpoints.node_pull_bind(self.node_id))
+        for peer in peers:
+            self._outbox(peer)
+        self.uplink = self.ctx.socket(zmq.PUSH)
+        self.uplink.connect(self.endpoints.monitor_pull_connect())
+        time.sleep(0.1)                                   # let the connects settle before the first round opens
+        return self
+
+    def _outbox(self, peer: int):
+        if peer not in self.outboxes:
+            out = self.ctx.socket(zmq.PUSH)
+            out.connect(self.endpoints.node_pull_connect(peer))
+            self.outboxes[peer] = out
+        return self.outboxes[peer]
+
+    def post(self, peer: int, frames) -> None:
+        self._outbox(peer).send_multipart(frames)
+
+    def report(self, frames) -> None:
+        self.uplink.send_multipart(frames)
+
+    def receive(self, timeout_ms: int):
+        """One decoded message ``(kind, sender, round, payload)`` or ``None`` after ``timeout_ms`` without traffic."""
+        if not self.inbox.poll(timeout=timeout_ms):
+            return None
+        return decode_full(self.inbox.recv_multipart())
+
+    def close(self) -> None:
+        for sock in (self.inbox, self.uplink, *self.outboxes.values()):
+            if sock is not None:
+                sock.close(linger=200)
+        self.outboxes.clear()
+        if self.ctx is not None:
+            self.ctx.term()
+            self.ctx = None
 
 
 class NodeProcess:
@@ -35,11 +86,8 @@ class NodeProcess:
     def __init__(self, node_id: int, config: Config, endpoints: Endpoints, t_start: float, mobility=None):
         self.node_id, self.config, self.endpoints, self.t_start = node_id, config, endpoints, t_start
         self.mobility = mobility
-        self._ctx: Optional[zmq.Context] = None
-        self._pull = None
-        self._push_socks: Dict[int, zmq.Socket] = {}
-        self._monitor_push = None
-        self._static_neighbors: Optional[List[int]] = None
+        self.mail = Mailbox(node_id, endpoints)
+        self._fixed_peers: Optional[List[int]] = None
 
     @classmethod
     def from_config_path(cls, node_id: int, config_path: str, endpoints: Endpoints, t_start: float):
@@ -50,47 +98,21 @@ class NodeProcess:
     # ---- lifecycle ------------------------------------------------------------------
     def run(self) -> None:
         set_seed(self.config.experiment.seed + self.node_id)
-        device = self._resolve_device()
-        node = self._build_node(device)
+        device = self._pick_device()
+        node = self._make_node(device)
         attack = build_attack(self.config)
         self._prepare(node, device)
-        self._ctx = zmq.Context()
         try:
-            self._setup_sockets()
-            self._run_all_rounds(node, attack)
+            self.mail.open(self._peer_universe())
+            self._round_loop(node, attack)
         finally:
-            self._teardown_sockets()
+            self.mail.close()
 
     def _prepare(self, node: Node, device: torch.device) -> None:
         """Hook for subclasses (DMTT) that need extra state before round 0."""
 
-    def _setup_sockets(self) -> None:
-        self._pull = self._ctx.socket(zmq.PULL)
-        self._pull.bind(self.endpoints.node_pull_bind(self.node_id))
-        for nid in self._get_static_neighbors():
-            self._ensure_push_sock(nid)
-        self._monitor_push = self._ctx.socket(zmq.PUSH)
-        self._monitor_push.connect(self.endpoints.monitor_pull_connect())
-        time.sleep(0.1)
-
-    def _ensure_push_sock(self, neighbor_id: int):
-        sock = self._push_socks.get(neighbor_id)
-        if sock is None:
-            sock = self._ctx.socket(zmq.PUSH)
-            sock.connect(self.endpoints.node_pull_connect(neighbor_id))
-            self._push_socks[neighbor_id] = sock
-        return sock
-
-    def _teardown_sockets(self) -> None:
-        for sock in (self._pull, self._monitor_push, *self._push_socks.values()):
-            if sock is not None:
-                sock.close(linger=200)
-        self._push_socks.clear()
-        if self._ctx is not None:
-            self._ctx.term()
-
     # ---- rounds ---------------------------------------------------------------------
-    def _run_all_rounds(self, node: Node, attack) -> None:
+    def _round_loop(self, node: Node, attack) -> None:
         dur = self.config.distributed.round_duration_s
         for r in range(self.config.experiment.rounds):
             opens = self.t_start + r * dur
@@ -98,7 +120,7 @@ class NodeProcess:
             if wait > 0:
                 time.sleep(wait)
             self._execute_round(node=node, attack=attack, round_idx=r, round_wall_end=opens + dur,
-                                current_neighbors=self._get_current_neighbors(r))
+                                current_neighbors=self._neighbors_in_round(r))
 
     def _outgoing_state(self, node: Node, attack, round_idx: int) -> ModelState:
         state = node.get_state()
@@ -115,7 +137,7 @@ class NodeProcess:
             print(f"[{self.log_tag} {self.node_id}] WARNING: training for round {round_idx + 1} exceeded "
                   f"round_duration_s={cfg.distributed.round_duration_s}s. Model exchange will be skipped.",
                   flush=True)
-            self._push_metrics(node, round_idx, skipped=True)
+            self._report(node, round_idx, skipped=True)
             return False
         return True
 
@@ -123,15 +145,15 @@ class NodeProcess:
                        current_neighbors: List[int]) -> None:
         if not self._train_or_skip(node, attack, round_idx, round_wall_end):
             return
-        blob = pack_state(self._outgoing_state(node, attack, round_idx))
-        for nid in current_neighbors:
-            self._ensure_push_sock(nid).send_multipart(encode(MsgType.MODEL_STATE, self.node_id, blob, round_idx))
-        received = self._collect_neighbor_states(current_neighbors, round_idx, round_wall_end)
+        frames = encode(MsgType.MODEL_STATE, self.node_id, pack_state(self._outgoing_state(node, attack, round_idx)), round_idx)
+        for peer in current_neighbors:                      # one serialisation, the same bytes to every neighbour
+            self.mail.post(peer, frames)
+        received = self._await_states(current_neighbors, round_idx, round_wall_end)
         if received:
             node.apply_aggregated_state(node.aggregate_with_neighbors(received, round_idx))
-        self._push_metrics(node, round_idx)
+        self._report(node, round_idx)
 
-    def _collect_neighbor_states(self, expected: List[int], round_idx: int, deadline: float) -> Dict[int, ModelState]:
+    def _await_states(self, expected: List[int], round_idx: int, deadline: float) -> Dict[int, ModelState]:
         got: Dict[int, ModelState] = {}
         want: Set[int] = set(expected)
         while len(got) < len(want):
@@ -140,50 +162,52 @@ class NodeProcess:
                 print(f"[{self.log_tag} {self.node_id}] Round {round_idx + 1}: deadline reached, missing states "
                       f"from {sorted(want - set(got))}. Aggregating with {len(got)}/{len(want)} neighbours.", flush=True)
                 break
-            if not self._pull.poll(timeout=max(50, left_ms)):
+            msg = self.mail.receive(max(50, left_ms))
+            if msg is None:
                 continue
-            kind, sender, rnd, payload = decode_full(self._pull.recv_multipart())
+            kind, sender, rnd, payload = msg
             if kind == MsgType.MODEL_STATE and sender in want and rnd in (-1, round_idx):
                 got[sender] = unpack_state(payload)
         return got
 
-    def _push_metrics(self, node: Node, round_idx: int, skipped: bool = False) -> None:
+    def _report(self, node: Node, round_idx: int, skipped: bool = False) -> None:
         metrics = {"accuracy": 0.0, "loss": 0.0, "skipped": True} if skipped else dict(node.evaluate())
         metrics["round_idx"] = round_idx
-        self._monitor_push.send_multipart(encode(MsgType.METRICS, self.node_id, pack_obj(metrics), round_idx))
+        self.mail.report(encode(MsgType.METRICS, self.node_id, pack_obj(metrics), round_idx))
 
     # ---- neighbours -----------------------------------------------------------------
-    def _get_static_neighbors(self) -> List[int]:
-        if self._static_neighbors is None:
+    def _peer_universe(self) -> List[int]:
+        """Every node this one may ever talk to (outboxes are connected up front): the static neighbours, or everybody
+        under mobility."""
+        if self._fixed_peers is None:
             n = self.config.topology.num_nodes
             if self.mobility is not None:
-                self._static_neighbors = [i for i in range(n) if i != self.node_id]
+                self._fixed_peers = [i for i in range(n) if i != self.node_id]
             else:
                 from murmura_b200.topology import create_topology
                 t = self.config.topology
-                self._static_neighbors = create_topology(t.type, n, p=t.p, k=t.k, seed=t.seed).neighbors[self.node_id]
-        return self._static_neighbors
+                self._fixed_peers = create_topology(t.type, n, p=t.p, k=t.k, seed=t.seed).neighbors[self.node_id]
+        return self._fixed_peers
 
-    def _get_current_neighbors(self, round_idx: int) -> List[int]:
+    def _neighbors_in_round(self, round_idx: int) -> List[int]:
         if self.mobility is not None:
             return self.mobility.neighbors_at(round_idx).get(self.node_id, [])
-        return self._get_static_neighbors()
+        return self._peer_universe()
 
     # ---- construction ---------------------------------------------------------------
-    def _resolve_device(self) -> torch.device:
+    def _pick_device(self) -> torch.device:
         from murmura_b200.utils.device import get_device
         dev = get_device()
         if dev.type == "cuda":      # pin node i → GPU i mod G (the reference piles everything on cuda:0)
             return torch.device("cuda", self.node_id % torch.cuda.device_count())
         return dev
 
-    def _build_node(self, device: torch.device) -> Node:
+    def _make_node(self, device: torch.device) -> Node:
         cfg = self.config
         adapter = build_dataset_adapter(cfg)
         model_factory = build_model_factory(cfg)
-        aggregator_factory = build_aggregator_factory(cfg, model_factory, device)
         criterion, evidential = build_criterion(cfg)
         train_loader, test_loader, _ = make_loaders(adapter, self.node_id, cfg.training.batch_size)
         return Node(node_id=self.node_id, model=model_factory().to(device), train_loader=train_loader, test_loader=test_loader,
-                    aggregator=aggregator_factory(self.node_id), device=device, criterion=criterion,
-                    evidential=evidential)
+                    aggregator=build_aggregator_factory(cfg, model_factory, device)(self.node_id), device=device,
+                    criterion=criterion, evidential=evidential)

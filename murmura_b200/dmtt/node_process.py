@@ -17,7 +17,7 @@ import torch.nn as nn
 from murmura_b200.config.loader import load_config
 from murmura_b200.config.schema import Config, DMTTConfig
 from murmura_b200.distributed.endpoints import Endpoints
-from murmura_b200.distributed.messaging import (MsgType, decode_full, encode, pack_obj, pack_state, unpack_obj,
+from murmura_b200.distributed.messaging import (MsgType, encode, pack_obj, pack_state, unpack_obj,
                                                 unpack_state)
 from murmura_b200.distributed.node_process import NodeProcess
 from murmura_b200.dmtt.state import DMTTNodeState
@@ -56,10 +56,10 @@ class DMTTNodeProcess(NodeProcess):
         self._eval_device = device
         self._dmtt = DMTTNodeState(self.node_id, self.dmtt_cfg, self.config.topology.num_nodes)
 
-    def _get_static_neighbors(self) -> List[int]:
+    def _peer_universe(self) -> List[int]:
         return [i for i in range(self.config.topology.num_nodes) if i != self.node_id]
 
-    def _get_current_neighbors(self, round_idx: int) -> List[int]:
+    def _neighbors_in_round(self, round_idx: int) -> List[int]:
         if round_idx == 0 or self._collaborators is None:
             return self.mobility.neighbors_at(0).get(self.node_id, [])
         return self._collaborators
@@ -76,10 +76,11 @@ class DMTTNodeProcess(NodeProcess):
         claimed = (attack.get_false_claims(node_id=self.node_id, true_neighbors=truth, round_num=round_idx)
                    if byz and hasattr(attack, "get_false_claims") else list(truth))
         claim_blob = pack_obj({"round_idx": round_idx, "neighbors": claimed})
+        state_frames = encode(MsgType.MODEL_STATE, self.node_id, state_blob, round_idx)
+        claim_frames = encode(MsgType.TOPO_CLAIM, self.node_id, claim_blob, round_idx)
         for nid in current_neighbors:
-            sock = self._ensure_push_sock(nid)
-            sock.send_multipart(encode(MsgType.MODEL_STATE, self.node_id, state_blob, round_idx))
-            sock.send_multipart(encode(MsgType.TOPO_CLAIM, self.node_id, claim_blob, round_idx))
+            self.mail.post(nid, state_frames)
+            self.mail.post(nid, claim_frames)
 
         states, claims = self._collect_dmtt_messages(current_neighbors, round_idx, round_wall_end)
         assert self._dmtt is not None
@@ -93,7 +94,7 @@ class DMTTNodeProcess(NodeProcess):
                                                model_scores=scores, B=self.dmtt_cfg.budget_B)
         if self.config.experiment.verbose:
             print(f"[DMTT Node {self.node_id}] Round {round_idx + 1}: collaborators → {self._collaborators}", flush=True)
-        self._push_metrics(node, round_idx)
+        self._report(node, round_idx)
 
     def _collect_dmtt_messages(self, expected: List[int], round_idx: int,
                                deadline: float) -> Tuple[Dict[int, Any], Dict[int, dict]]:
@@ -106,9 +107,10 @@ class DMTTNodeProcess(NodeProcess):
                 print(f"[DMTT Node {self.node_id}] Round {round_idx + 1}: deadline — missing states from "
                       f"{sorted(want - set(states))}, claims from {sorted(want - set(claims))}.", flush=True)
                 break
-            if not self._pull.poll(timeout=max(50, left_ms)):
+            msg = self.mail.receive(max(50, left_ms))
+            if msg is None:
                 continue
-            kind, sender, rnd, payload = decode_full(self._pull.recv_multipart())
+            kind, sender, rnd, payload = msg
             if sender not in want or rnd not in (-1, round_idx):
                 continue
             if kind == MsgType.MODEL_STATE and sender not in states:
