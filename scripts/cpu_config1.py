@@ -9,9 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(arm, rounds, nodes, algo):
+def run(arm, rounds, nodes, algo, topo="ring"):
     import torch
-    d = {"experiment": {"name": "cfg1", "seed": 42, "rounds": rounds + 2}, "topology": {"type": "ring", "num_nodes": nodes},
+    d = {"experiment": {"name": "cfg1", "seed": 42, "rounds": rounds + 2}, "topology": {"type": topo, "num_nodes": nodes, "p": 0.3, "k": 4, "seed": 7},
          "aggregation": {"algorithm": algo, "params": {}}, "training": {"local_epochs": 1, "batch_size": 64, "lr": 0.01}}
     if arm == "reference":
         sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
@@ -40,19 +40,19 @@ def run(arm, rounds, nodes, algo):
         t0 = time.perf_counter()
         h = net.train(rounds=rounds, local_epochs=1, lr=0.01)
         dt = time.perf_counter() - t0
-    return {"arm": arm, "nodes": nodes, "algo": algo, "rounds": rounds, "rounds_per_s": round(rounds / dt, 2), "ms_per_round": round(dt / rounds * 1e3, 1),
+    return {"arm": arm, "nodes": nodes, "algo": algo, "topology": topo, "rounds": rounds, "rounds_per_s": round(rounds / dt, 2), "ms_per_round": round(dt / rounds * 1e3, 1),
             "final_acc": round(float(h["mean_accuracy"][-1]), 4), "threads": torch.get_num_threads()}
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=20); ap.add_argument("--arm", default="both"); ap.add_argument("--nodes", type=int, default=2)
-    ap.add_argument("--algo", default="fedavg")
+    ap.add_argument("--algo", default="fedavg"); ap.add_argument("--topo", default="ring")
     a = ap.parse_args()
     for arm in (("ours", "reference") if a.arm == "both" else (a.arm,)):
         if a.arm == "both":            # separate interpreters: both packages patch global RNG / thread state
             import subprocess
-            print(subprocess.run([sys.executable, __file__, "--rounds", str(a.rounds), "--arm", arm, "--nodes", str(a.nodes), "--algo", a.algo],
+            print(subprocess.run([sys.executable, __file__, "--rounds", str(a.rounds), "--arm", arm, "--nodes", str(a.nodes), "--algo", a.algo, "--topo", a.topo],
                                  capture_output=True, text=True).stdout.strip())
         else:
-            print(json.dumps(run(arm, a.rounds, a.nodes, a.algo)))
+            print(json.dumps(run(arm, a.rounds, a.nodes, a.algo, a.topo)))
