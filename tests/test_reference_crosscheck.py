@@ -244,3 +244,59 @@ def test_simulation_training_history_identical_to_reference(algo, params, attack
             if np.isnan(float(u)) and np.isnan(float(v)):            # λ = −5 models diverge to NaN loss in both implementations
                 continue
             assert abs(float(u) - float(v)) <= 1e-6 * max(1.0, abs(float(u))), (k, u, v)     # fp32 summation order only
+
+
+def _write_uci_har(root, n=180, subjects=6, seed=0):
+    rng = np.random.RandomState(seed)
+    for split in ("train", "test"):
+        d = root / split
+        d.mkdir(parents=True, exist_ok=True)
+        np.savetxt(d / f"X_{split}.txt", rng.randn(n, 561).astype(np.float32), fmt="%.6e")
+        np.savetxt(d / f"y_{split}.txt", rng.randint(1, 7, size=n), fmt="%d")
+        np.savetxt(d / f"subject_{split}.txt", np.sort(rng.randint(1, subjects + 1, size=n)), fmt="%d")
+
+
+@pytest.mark.parametrize("method", ["dirichlet", "iid", "natural"])
+def test_wearable_adapter_on_uci_har_files_identical(tmp_path, method):
+    """Real-format UCI-HAR files → same tensors and the same client partitions as the reference loader, for every
+    partitioning strategy."""
+    from murmura.examples.wearables.adapter import load_wearable_adapter as ref_load
+    from murmura_b200.examples.wearables.adapter import load_wearable_adapter as our_load
+    _write_uci_har(tmp_path)
+    kw = dict(dataset_type="uci_har", data_path=str(tmp_path), num_nodes=4, partition_method=method, alpha=0.5, seed=42)
+    a, b = ref_load(**kw), our_load(**kw)
+    pa, pb = a.get_client_partitions(), b.get_client_partitions()
+    assert [sorted(map(int, p)) for p in pa] == [sorted(map(int, p)) for p in pb]
+    for cid in range(len(pa)):
+        if not len(pa[cid]):
+            continue
+        xa, ya = a.get_client_data(cid)[0]
+        xb, yb = b.get_client_data(cid)[0]
+        assert torch.equal(torch.as_tensor(xa), torch.as_tensor(xb)) and int(ya) == int(yb)
+    assert len(a.dataset) == len(b.dataset)
+
+
+def test_leaf_partitions_identical(tmp_path):
+    """LEAF FEMNIST JSON shards → same user → node assignment and the same sample order as the reference."""
+    import json
+    from murmura.examples.leaf.datasets import LEAFFEMNISTDataset as RefDS, create_leaf_client_partitions as ref_parts
+    from murmura_b200.examples.leaf.datasets import LEAFFEMNISTDataset, create_leaf_client_partitions
+    rng = np.random.RandomState(1)
+    users = [f"u{i:02d}" for i in range(9)]
+    for split, scale in (("train", 1), ("test", 1)):
+        d = tmp_path / split
+        d.mkdir()
+        counts = {u: int(rng.randint(3, 9)) for u in users}
+        blob = {"users": users, "num_samples": [counts[u] for u in users],
+                "user_data": {u: {"x": rng.rand(counts[u], 784).round(4).tolist(), "y": rng.randint(0, 62, size=counts[u]).tolist()} for u in users}}
+        (d / "all_data_0.json").write_text(json.dumps(blob))
+    ra_tr, ra_te = RefDS(str(tmp_path), split="train"), RefDS(str(tmp_path), split="test")
+    ob_tr, ob_te = LEAFFEMNISTDataset(str(tmp_path), split="train"), LEAFFEMNISTDataset(str(tmp_path), split="test")
+    assert len(ra_tr) == len(ob_tr)
+    for nodes in (2, 4):
+        pr = ref_parts(ra_tr, ra_te, num_nodes=nodes, seed=42)
+        po = create_leaf_client_partitions(ob_tr, ob_te, num_nodes=nodes, seed=42)
+        assert [[list(map(int, p)) for p in side] for side in pr] == [[list(map(int, p)) for p in side] for side in po]
+    xa, ya = ra_tr[3]; xb, yb = ob_tr[3]                     # reference: 8-bit PIL image (no transform); ours: float tensor [1, 28, 28]
+    ref_pixels = torch.from_numpy(np.asarray(xa, dtype=np.float32) / 255.0).reshape(-1)
+    assert torch.allclose(ref_pixels, torch.as_tensor(xb).float().reshape(-1), atol=1.0 / 255 + 1e-6) and int(ya) == int(yb)
