@@ -300,3 +300,87 @@ def test_leaf_partitions_identical(tmp_path):
     xa, ya = ra_tr[3]; xb, yb = ob_tr[3]                     # reference: 8-bit PIL image (no transform); ours: float tensor [1, 28, 28]
     ref_pixels = torch.from_numpy(np.asarray(xa, dtype=np.float32) / 255.0).reshape(-1)
     assert torch.allclose(ref_pixels, torch.as_tensor(xb).float().reshape(-1), atol=1.0 / 255 + 1e-6) and int(ya) == int(yb)
+
+
+def test_pamap2_loader_identical_on_protocol_files(tmp_path):
+    """Real-format PAMAP2 ``Protocol/subject10X.dat`` files (54 columns, NaNs, transient activity 0) → identical windows, labels,
+    subject ids and normalisation as the reference's loader."""
+    from murmura.examples.wearables.datasets import PAMAP2Dataset as RefPAMAP2
+    from murmura_b200.examples.wearables.datasets import PAMAP2Dataset
+    rng = np.random.RandomState(3)
+    proto = tmp_path / "Protocol"
+    proto.mkdir()
+    acts = np.array([0, 1, 2, 4, 12, 24, 9])                       # 0 = transient, 9 = not in the 12-class subset
+    for sid in (101, 102, 105):
+        rows = 460
+        data = rng.randn(rows, 54)
+        data[:, 0] = np.arange(rows) * 0.01
+        data[:, 1] = np.repeat(acts[rng.randint(0, len(acts), size=rows // 20)], 20)
+        data[rng.rand(rows) < 0.3, 2] = np.nan                      # heart rate is sampled at ~9 Hz: mostly NaN in the real files
+        data[rng.rand(rows, 54) < 0.01] = np.nan
+        data[:, 1] = np.nan_to_num(data[:, 1])
+        np.savetxt(proto / f"subject{sid}.dat", data, fmt="%.5f")
+    kw = dict(root=str(tmp_path), window_size=20, window_stride=10)
+    a, b = RefPAMAP2(**kw), PAMAP2Dataset(**kw)
+    assert len(a) == len(b) > 10
+    assert np.array_equal(a.get_labels(), b.get_labels()) and np.array_equal(a.get_subjects(), b.get_subjects())
+    fa = torch.stack([a[i][0] for i in range(len(a))]); fb = torch.stack([b[i][0] for i in range(len(b))])
+    assert fa.shape == fb.shape and torch.allclose(fa, fb, atol=1e-5, rtol=1e-5)
+    assert a.num_features == b.num_features and a.num_classes == b.num_classes
+
+
+def test_ppg_dalia_loader_identical_on_pickles(tmp_path):
+    """Real-format PPG-DaLiA ``S<k>/S<k>.pkl`` files (wrist EDA/TEMP @4 Hz, ACC @32 Hz, BVP @64 Hz, activity @4 Hz) → identical
+    features, labels and subject ids as the reference's loader."""
+    import pickle
+    from murmura.examples.wearables.datasets import PPGDaLiADataset as RefPPG
+    from murmura_b200.examples.wearables.datasets import PPGDaLiADataset
+    rng = np.random.RandomState(5)
+    for sid in (1, 2, 7):
+        t = 400 + 8 * sid                                            # 4 Hz samples
+        act = np.repeat(rng.randint(0, 9, size=t // 16 + 1), 16)[:t].astype(float).reshape(-1, 1)     # 0 = transient, 8 = outside 1–7
+        eda = rng.rand(t, 1); eda[rng.rand(t) < 0.02] = np.nan
+        blob = {"activity": act, "signal": {"wrist": {"EDA": eda, "TEMP": 30 + rng.rand(t + 3, 1), "ACC": rng.randn(t * 8 + 5, 3),
+                                                       "BVP": rng.randn(t * 16 + 11, 1)}}}
+        d = tmp_path / f"S{sid}"
+        d.mkdir()
+        with open(d / f"S{sid}.pkl", "wb") as fh:
+            pickle.dump(blob, fh, protocol=2)
+    a, b = RefPPG(root=str(tmp_path)), PPGDaLiADataset(root=str(tmp_path))
+    assert len(a) == len(b) > 10 and a.num_features == b.num_features == 192 and a.num_classes == b.num_classes
+    assert np.array_equal(a.get_labels(), b.get_labels()) and np.array_equal(a.get_subjects(), b.get_subjects())
+    fa = torch.stack([a[i][0] for i in range(len(a))]); fb = torch.stack([b[i][0] for i in range(len(b))])
+    assert torch.allclose(fa, fb, atol=1e-5, rtol=1e-5)
+
+
+def test_node_training_and_evaluation_identical():
+    """``Node.local_train`` + ``Node.evaluate`` (plain and evidential): same weights, same loader, same seed → same state and
+    the same metric dict as the reference's Node."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from murmura.core.node import Node as RefNode
+    from murmura.aggregation import FedAvgAggregator as RefFedAvg
+    from murmura.examples.wearables.models import EvidentialHARClassifier as RefHAR, EvidentialLoss as RefLoss
+    from murmura_b200.core.node import Node
+    from murmura_b200.aggregation import FedAvgAggregator
+    from murmura_b200.models.mlp import EvidentialHARClassifier, EvidentialLoss
+    torch.manual_seed(0)
+    x = torch.randn(96, 24); y = torch.randint(0, 5, (96,))
+    kw = dict(input_dim=24, hidden_dims=[16, 8], num_classes=5, dropout=0.2)
+    for evidential in (True, False):
+        mr = RefHAR(**kw); mo = EvidentialHARClassifier(**kw); mo.load_state_dict(mr.state_dict())
+        mk = lambda: DataLoader(TensorDataset(x, y), batch_size=32, shuffle=True, drop_last=True)
+        ev = lambda: DataLoader(TensorDataset(x, y), batch_size=32, shuffle=False)
+        crit_r = RefLoss(num_classes=5, annealing_epochs=5, lambda_weight=0.1) if evidential else None
+        crit_o = EvidentialLoss(num_classes=5, annealing_epochs=5, lambda_weight=0.1) if evidential else None
+        nr = RefNode(node_id=0, model=mr, train_loader=mk(), test_loader=ev(), aggregator=RefFedAvg(), device=torch.device("cpu"),
+                     criterion=crit_r, evidential=evidential)
+        no = Node(node_id=0, model=mo, train_loader=mk(), test_loader=ev(), aggregator=FedAvgAggregator(), device=torch.device("cpu"),
+                  criterion=crit_o, evidential=evidential)
+        for rnd in range(2):
+            torch.manual_seed(100 + rnd); nr.local_train(epochs=2, lr=0.05, round_num=rnd)
+            torch.manual_seed(100 + rnd); no.local_train(epochs=2, lr=0.05, round_num=rnd)
+        _same(nr.get_state(), no.get_state(), atol=1e-6)
+        er, eo = nr.evaluate(), no.evaluate()
+        assert er.keys() == eo.keys()
+        for k in er:
+            assert abs(float(er[k]) - float(eo[k])) <= 1e-5 * max(1.0, abs(float(er[k]))), (evidential, k, er[k], eo[k])
