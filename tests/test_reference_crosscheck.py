@@ -384,3 +384,66 @@ def test_node_training_and_evaluation_identical():
         assert er.keys() == eo.keys()
         for k in er:
             assert abs(float(er[k]) - float(eo[k])) <= 1e-5 * max(1.0, abs(float(er[k]))), (evidential, k, er[k], eo[k])
+
+
+def test_monitor_round_records_and_log_lines_identical(capsys):
+    """The monitor's per-round bookkeeping (`_record`): same history dict and byte-identical `[Monitor] …` lines as the
+    reference, with honest / compromised splits, evidential metrics and partial rounds."""
+    from murmura.distributed.monitor import Monitor as RefMonitor
+    from murmura_b200.distributed.monitor import Monitor
+    rng = random.Random(8)
+    rounds = []
+    for r in range(1, 5):
+        nodes = [i for i in range(6) if not (r == 3 and i in (1, 4))]            # round 3: two nodes missed the deadline
+        rounds.append((r, {i: {"accuracy": rng.random(), "loss": rng.random() * 2,
+                               **({"vacuity": rng.random(), "entropy": rng.random(), "strength": 5 + rng.random()} if r != 2 else {})}
+                           for i in nodes}))
+    outs = []
+    for cls in (RefMonitor, Monitor):
+        m = cls(num_nodes=6, endpoints=None, rounds=4, t_start=0.0, round_duration_s=1.0, compromised_nodes={1, 5}, verbose=True)
+        for r, metrics in rounds:
+            m._record(r, metrics)
+        outs.append((m.history, capsys.readouterr().out))
+    (ha, la), (hb, lb) = outs
+    assert la == lb and la.count("[Monitor] Round") == 4
+    assert ha.keys() == hb.keys()
+    for k in ha:
+        assert len(ha[k]) == len(hb[k]) and all(abs(float(u) - float(v)) < 1e-12 for u, v in zip(ha[k], hb[k])), k
+
+
+def test_stdout_contract_byte_identical(capsys):
+    """What the experiment harness scrapes: the attack banner, `=== Round k/K ===`, `Round k: Mean Accuracy = …`, `Honest: …`
+    and `Uncertainty: …` lines printed by ``Network.train(verbose=True)`` are byte-identical to the reference's."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    texts = []
+    for arm in ("reference", "ours"):
+        d = {"experiment": {"name": "x", "seed": 42, "rounds": 2}, "topology": {"type": "fully", "num_nodes": 5},
+             "aggregation": {"algorithm": "evidential_trust", "params": {"trust_threshold": 0.1}},
+             "attack": {"enabled": True, "type": "gaussian", "percentage": 0.2, "params": {"noise_std": 10.0}},
+             "training": {"local_epochs": 1, "batch_size": 32, "lr": 0.01},
+             "model": {"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6}}}
+        if arm == "reference":
+            from murmura.config import Config
+            from murmura.core.network import Network
+            from murmura.utils.factories import build_aggregator_factory, build_criterion, build_dataset_adapter, build_model_factory
+            from murmura.utils.seed import set_seed
+            d["data"] = {"adapter": "baseline.ref_workloads.SyntheticRefAdapter",
+                         "params": {"name": "uci_har", "num_nodes": 5, "samples_per_node": 64, "alpha": 0.5, "seed": 42}}
+        else:
+            from murmura_b200.config import Config
+            from murmura_b200.core.network import Network
+            from murmura_b200.utils.factories import build_aggregator_factory, build_criterion, build_dataset_adapter, build_model_factory
+            from murmura_b200.utils.seed import set_seed
+            d["data"] = {"adapter": "synthetic.uci_har", "params": {"samples_per_node": 64, "partition_method": "dirichlet", "alpha": 0.5}}
+            d["backend"] = "simulation"
+        cfg = Config(**d)
+        set_seed(42)
+        dev = torch.device("cpu")
+        adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg); crit, evid = build_criterion(cfg)
+        capsys.readouterr()                                        # adapters may print their own summaries: not part of the contract
+        net = Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf, dev), device=dev, criterion=crit, evidential=evid)
+        net.train(rounds=2, local_epochs=1, lr=0.01, verbose=True)
+        texts.append(capsys.readouterr().out)
+    assert texts[0] == texts[1]
+    assert "Round 2: Mean Accuracy = " in texts[0] and "Honest:" in texts[0] and "Uncertainty: Vacuity=" in texts[0] and "Compromised" in texts[0]
