@@ -447,3 +447,35 @@ def test_stdout_contract_byte_identical(capsys):
         texts.append(capsys.readouterr().out)
     assert texts[0] == texts[1]
     assert "Round 2: Mean Accuracy = " in texts[0] and "Honest:" in texts[0] and "Uncertainty: Vacuity=" in texts[0] and "Compromised" in texts[0]
+
+
+def test_config_schema_defaults_and_factories_identical():
+    """Same YAML dict → same validated config on every field the reference knows (ours adds ``b200``), and the factories build
+    equally parameterised aggregators / criteria / attacks / mobility models."""
+    from murmura.config import Config as RefConfig
+    from murmura.utils import factories as rf
+    from murmura_b200.config import Config
+    from murmura_b200.utils import factories as of
+    base = {"experiment": {"name": "x", "rounds": 30}, "topology": {"type": "k-regular", "num_nodes": 12, "k": 4},
+            "aggregation": {"algorithm": "sketchguard", "params": {"sketch_size": 128}},
+            "training": {}, "data": {"adapter": "wearables.uci_har", "params": {"data_path": "synthetic"}},
+            "model": {"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6}},
+            "attack": {"enabled": True, "type": "topology_liar", "percentage": 0.25, "params": {"model_attack_type": "gaussian", "noise_std": 3.0}},
+            "mobility": {"comm_range": 35.0}, "dmtt": {"budget_B": 4}, "backend": "distributed", "distributed": {"transport": "tcp"}}
+    a, b = RefConfig(**base).model_dump(), Config(**base).model_dump()
+    b.pop("b200")
+    assert a == b
+    ra, oa = RefConfig(**base), Config(**base)
+    mf_r, mf_o = rf.build_model_factory(ra), of.build_model_factory(oa)
+    assert [tuple(p.shape) for p in mf_r().parameters()] == [tuple(p.shape) for p in mf_o().parameters()]
+    cpu = torch.device("cpu")
+    ag_r, ag_o = rf.build_aggregator_factory(ra, mf_r, cpu)(3), of.build_aggregator_factory(oa, mf_o, cpu)(3)
+    for attr in ("model_dim", "sketch_size", "gamma", "kappa", "alpha", "min_neighbors", "total_rounds", "network_seed"):
+        assert getattr(ag_r, attr) == getattr(ag_o, attr), attr
+    (cr, er), (co, eo) = rf.build_criterion(ra), of.build_criterion(oa)
+    assert er == eo and (cr.num_classes, cr.annealing_epochs, cr.lambda_weight) == (co.num_classes, co.annealing_epochs, co.lambda_weight)
+    at_r, at_o = rf.build_attack(ra), of.build_attack(oa)
+    assert type(at_r).__name__ == type(at_o).__name__ == "TopologyLiarAttack"
+    assert sorted(at_r.get_compromised_nodes()) == sorted(at_o.get_compromised_nodes())
+    mob_r, mob_o = rf.build_mobility_model(ra), of.build_mobility_model(oa)
+    assert {i: sorted(v) for i, v in mob_r.neighbors_at(2).items()} == {i: sorted(v) for i, v in mob_o.neighbors_at(2).items()}
