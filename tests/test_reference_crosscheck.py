@@ -479,3 +479,51 @@ def test_config_schema_defaults_and_factories_identical():
     assert sorted(at_r.get_compromised_nodes()) == sorted(at_o.get_compromised_nodes())
     mob_r, mob_o = rf.build_mobility_model(ra), of.build_mobility_model(oa)
     assert {i: sorted(v) for i, v in mob_r.neighbors_at(2).items()} == {i: sorted(v) for i, v in mob_o.neighbors_at(2).items()}
+
+
+_DIST_HELPER = r"""
+import json, os, sys, tempfile
+import yaml
+ROOT, arm = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ROOT)
+d = {"experiment": {"name": "x", "seed": 42, "rounds": 2, "verbose": False}, "topology": {"type": "ring", "num_nodes": 3},
+     "aggregation": {"algorithm": "fedavg", "params": {}}, "training": {"local_epochs": 1, "batch_size": 32, "lr": 0.01},
+     "model": {"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6}},
+     "backend": "distributed", "distributed": {"transport": "ipc", "round_duration_s": 6.0, "startup_grace_s": 4.0}}
+if arm == "reference":
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    from murmura.distributed import DistributedRunner
+    d["data"] = {"adapter": "baseline.ref_workloads.SyntheticRefAdapter",
+                 "params": {"name": "uci_har", "num_nodes": 3, "samples_per_node": 64, "alpha": 0.5, "seed": 42}}
+else:
+    from murmura_b200.distributed import DistributedRunner
+    d["data"] = {"adapter": "synthetic.uci_har", "params": {"samples_per_node": 64, "partition_method": "dirichlet", "alpha": 0.5}}
+path = tempfile.mktemp(suffix=".yaml")
+yaml.safe_dump(d, open(path, "w"))
+if __name__ == "__main__":
+    h = DistributedRunner(path).run()
+    print("HIST", json.dumps({k: [float(x) for x in v] for k, v in h.items()}))
+"""
+
+
+@pytest.mark.timeout(400)
+def test_zeromq_backend_history_identical_to_reference(tmp_path):
+    """The wall-clock ZeroMQ backend end to end (monitor + 3 node processes over ipc://): same per-node seeds, same shards, same
+    exchange semantics → the monitor's history equals the reference backend's to fp32 round-off."""
+    import json
+    import subprocess
+    helper = tmp_path / "dist_cross.py"
+    helper.write_text(_DIST_HELPER)
+    hist = {}
+    for arm in ("reference", "ours"):
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT] + ([REF] if arm == "reference" else [])))
+        res = subprocess.run([sys.executable, str(helper), ROOT, arm], capture_output=True, text=True, timeout=180, env=env, cwd=str(tmp_path))
+        line = next((l for l in res.stdout.splitlines() if l.startswith("HIST ")), None)
+        assert res.returncode == 0 and line, res.stdout[-1500:] + res.stderr[-1500:]
+        hist[arm] = json.loads(line[5:])
+    a, b = hist["reference"], hist["ours"]
+    assert a.keys() == b.keys() and a["round"] == b["round"] == [1.0, 2.0]
+    for k in a:
+        assert len(a[k]) == len(b[k]), k
+        for u, v in zip(a[k], b[k]):
+            assert abs(u - v) <= 1e-6 * max(1.0, abs(u)), (k, u, v)
