@@ -484,17 +484,24 @@ def test_config_schema_defaults_and_factories_identical():
 _DIST_HELPER = r"""
 import json, os, sys, tempfile
 import yaml
-ROOT, arm = sys.argv[1], sys.argv[2]
+ROOT, arm, mode = sys.argv[1], sys.argv[2], sys.argv[3]
 sys.path.insert(0, ROOT)
-d = {"experiment": {"name": "x", "seed": 42, "rounds": 2, "verbose": False}, "topology": {"type": "ring", "num_nodes": 3},
+N = 3 if mode == "plain" else 5
+d = {"experiment": {"name": "x", "seed": 42, "rounds": 2 if mode == "plain" else 3, "verbose": False},
+     "topology": {"type": "ring" if mode == "plain" else "fully", "num_nodes": N},
      "aggregation": {"algorithm": "fedavg", "params": {}}, "training": {"local_epochs": 1, "batch_size": 32, "lr": 0.01},
      "model": {"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6}},
-     "backend": "distributed", "distributed": {"transport": "ipc", "round_duration_s": 6.0, "startup_grace_s": 4.0}}
+     "backend": "distributed", "distributed": {"transport": "ipc", "round_duration_s": 6.0 if mode == "plain" else 8.0,
+                                               "startup_grace_s": 4.0 if mode == "plain" else 5.0}}
+if mode == "dmtt":      # mobility-driven G^t, 25 % topology liars wrapping a Gaussian model attack, Top-2 collaborator selection
+    d["attack"] = {"enabled": True, "type": "topology_liar", "percentage": 0.25, "params": {"model_attack_type": "gaussian", "noise_std": 10.0}}
+    d["mobility"] = {"area_size": 100.0, "comm_range": 60.0, "max_speed": 8.0, "seed": 42, "ensure_connected": True}
+    d["dmtt"] = {"budget_B": 2}
 if arm == "reference":
     sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
     from murmura.distributed import DistributedRunner
     d["data"] = {"adapter": "baseline.ref_workloads.SyntheticRefAdapter",
-                 "params": {"name": "uci_har", "num_nodes": 3, "samples_per_node": 64, "alpha": 0.5, "seed": 42}}
+                 "params": {"name": "uci_har", "num_nodes": N, "samples_per_node": 64, "alpha": 0.5, "seed": 42}}
 else:
     from murmura_b200.distributed import DistributedRunner
     d["data"] = {"adapter": "synthetic.uci_har", "params": {"samples_per_node": 64, "partition_method": "dirichlet", "alpha": 0.5}}
@@ -506,24 +513,29 @@ if __name__ == "__main__":
 """
 
 
-@pytest.mark.timeout(400)
-def test_zeromq_backend_history_identical_to_reference(tmp_path):
-    """The wall-clock ZeroMQ backend end to end (monitor + 3 node processes over ipc://): same per-node seeds, same shards, same
-    exchange semantics → the monitor's history equals the reference backend's to fp32 round-off."""
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("mode", ["plain", "dmtt"])
+def test_zeromq_backend_history_identical_to_reference(tmp_path, mode):
+    """The wall-clock ZeroMQ backend end to end (monitor + node processes over ipc://): same per-node seeds, same shards, same
+    exchange semantics → the monitor's history equals the reference backend's to fp32 round-off.  ``dmtt`` adds the mobility
+    model, topology liars, claim verification, trust updates and Top-B collaborator selection of ``DMTTNodeProcess``."""
     import json
+    import math
     import subprocess
     helper = tmp_path / "dist_cross.py"
     helper.write_text(_DIST_HELPER)
     hist = {}
     for arm in ("reference", "ours"):
         env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT] + ([REF] if arm == "reference" else [])))
-        res = subprocess.run([sys.executable, str(helper), ROOT, arm], capture_output=True, text=True, timeout=180, env=env, cwd=str(tmp_path))
+        res = subprocess.run([sys.executable, str(helper), ROOT, arm, mode], capture_output=True, text=True, timeout=280, env=env, cwd=str(tmp_path))
         line = next((l for l in res.stdout.splitlines() if l.startswith("HIST ")), None)
         assert res.returncode == 0 and line, res.stdout[-1500:] + res.stderr[-1500:]
         hist[arm] = json.loads(line[5:])
     a, b = hist["reference"], hist["ours"]
-    assert a.keys() == b.keys() and a["round"] == b["round"] == [1.0, 2.0]
+    assert a.keys() == b.keys() and a["round"] == b["round"] and len(a["round"]) == (2 if mode == "plain" else 3)
     for k in a:
         assert len(a[k]) == len(b[k]), k
         for u, v in zip(a[k], b[k]):
-            assert abs(u - v) <= 1e-6 * max(1.0, abs(u)), (k, u, v)
+            if math.isnan(u) and math.isnan(v):                   # a compromised model evaluated to NaN loss in both
+                continue
+            assert abs(u - v) <= 1e-5 * max(1.0, abs(u)), (k, u, v)
