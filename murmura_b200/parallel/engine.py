@@ -1503,7 +1503,9 @@ class B200Network:
     def close(self) -> None:
         torch.cuda.synchronize()
         for vn in self.nodes:
-            vn.train_graph = None; vn.eval_graph = None
+            vn.train_graph = None; vn.eval_graph = None; vn.split_bwd = None
+        self._evaluators.clear()                      # CUDA graphs / views that point into the arena must go before it does
+        self.__dict__.pop("_batched_cache", None)
         if self.world > 1:
             _dist().barrier()
         self.arena.close()
