@@ -111,6 +111,18 @@ def test_partitioners_identical():
         assert [sorted(map(int, x)) for x in a] == [sorted(map(int, x)) for x in b]
     a, b = ref_iid(1000, 7, seed=3), iid_partition(1000, 7, seed=3)
     assert [list(map(int, x)) for x in a] == [list(map(int, x)) for x in b]
+    from murmura.data.partitioners import combine_partitions_with_dirichlet as ref_combine, natural_partition as ref_natural
+    from murmura_b200.data.partitioners import combine_partitions_with_dirichlet, natural_partition
+    ids = np.random.RandomState(2).choice([3, 7, 11, 20, 42, 43], size=500)
+    for limit in (None, 4):
+        (pa, na), (pb, nb) = ref_natural(ids, limit), natural_partition(ids, limit)
+        assert na == nb and [list(map(int, x)) for x in pa] == [list(map(int, x)) for x in pb]
+    nat, _ = ref_natural(ids)
+    lab = labels[:500]
+    for clients, alpha in ((3, 0.3), (8, 1.0)):
+        ca = ref_combine(nat, lab, clients, alpha=alpha, seed=5)
+        cb = combine_partitions_with_dirichlet(nat, lab, clients, alpha=alpha, seed=5)
+        assert [sorted(map(int, x)) for x in ca] == [sorted(map(int, x)) for x in cb]
 
 
 def test_mobility_model_identical():
