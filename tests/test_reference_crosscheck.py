@@ -555,3 +555,35 @@ def test_zeromq_backend_history_identical_to_reference(tmp_path, mode):
             # protocol difference (wrong collaborators, missed messages, different trust) moves these numbers by far more.
             tol = 0.02 if "accuracy" in k else 0.03 * max(1.0, abs(u))
             assert abs(u - v) <= tol, (k, u, v)
+
+
+def test_bundled_models_and_losses_identical():
+    """Every bundled architecture has the reference's state-dict (keys, shapes) and — with the reference's weights loaded —
+    the same outputs; ``EvidentialLoss`` / ``compute_uncertainty`` give the same numbers."""
+    import murmura.examples.leaf.models as rlm
+    import murmura.examples.leaf.datasets as rld
+    import murmura.examples.wearables.models as rwm
+    import murmura_b200.examples.leaf.models as olm
+    import murmura_b200.examples.wearables.models as owm
+    from murmura_b200.models.cnn import LEAFCelebAModel, LEAFFEMNISTModel
+    torch.manual_seed(0)
+    pairs = [(rlm.get_model_variant(v), olm.get_model_variant(v), torch.randn(2, 1, 28, 28)) for v in ("tiny", "small", "baseline")]
+    pairs += [(rld.LEAFFEMNISTModel(), LEAFFEMNISTModel(), torch.randn(2, 1, 28, 28)), (rld.LEAFCelebAModel(), LEAFCelebAModel(), torch.randn(2, 3, 84, 84))]
+    pairs += [(rwm.create_har_model(), owm.create_har_model(), torch.randn(4, 561)),
+              (rwm.create_ppg_dalia_model(), owm.create_ppg_dalia_model(), torch.randn(4, 192)),
+              (rwm.create_pamap2_model(), owm.create_pamap2_model(), torch.randn(4, 4000))]
+    for ref_m, our_m, x in pairs:
+        sr, so = ref_m.state_dict(), our_m.state_dict()
+        assert list(sr) == list(so) and all(sr[k].shape == so[k].shape for k in sr), type(ref_m).__name__
+        our_m.load_state_dict(sr)
+        ref_m.eval(); our_m.eval()
+        with torch.no_grad():
+            assert torch.allclose(ref_m(x), our_m(x), atol=1e-5, rtol=1e-5), type(ref_m).__name__
+    alpha = torch.rand(16, 6) * 5 + 1
+    y = torch.randint(0, 6, (16,))
+    ur, uo = rwm.compute_uncertainty(alpha), owm.compute_uncertainty(alpha)
+    assert ur.keys() == uo.keys() and all(torch.allclose(ur[k], uo[k], atol=1e-6) for k in ur)
+    for epoch in (0, 3, 10, 40):
+        lr_ = rwm.EvidentialLoss(num_classes=6, annealing_epochs=10, lambda_weight=0.5)(alpha, y, epoch=epoch)
+        lo_ = owm.EvidentialLoss(num_classes=6, annealing_epochs=10, lambda_weight=0.5)(alpha, y, epoch=epoch)
+        assert abs(float(lr_) - float(lo_)) < 1e-5, epoch
