@@ -504,7 +504,7 @@ d = {"experiment": {"name": "x", "seed": 42, "rounds": 2 if mode == "plain" else
      "aggregation": {"algorithm": "fedavg", "params": {}}, "training": {"local_epochs": 1, "batch_size": 32, "lr": 0.01},
      "model": {"factory": "examples.wearables.uci_har", "params": {"input_dim": 561, "num_classes": 6}},
      "backend": "distributed", "distributed": {"transport": "ipc", "round_duration_s": 8.0 if mode == "plain" else 10.0,      # generous: a missed deadline
-                                               "startup_grace_s": 5.0 if mode == "plain" else 6.0}}         # would change the history
+                                               "startup_grace_s": 12.0}}                                   # or a late start would change the history
 if mode == "dmtt":      # mobility-driven G^t, 25 % topology liars wrapping a Gaussian model attack, Top-2 collaborator selection
     d["attack"] = {"enabled": True, "type": "topology_liar", "percentage": 0.25, "params": {"model_attack_type": "gaussian", "noise_std": 10.0}}
     d["mobility"] = {"area_size": 100.0, "comm_range": 60.0, "max_speed": 8.0, "seed": 42, "ensure_connected": True}
