@@ -1,0 +1,205 @@
+"""Launch plans for ``conv_tcgen05.cu`` (grouped implicit-GEMM conv / linear layers) + a NumPy emulator of the kernel's addressing.
+
+A plan is a plain ``dict`` whose keys are the fields of ``ConvGemmParams``; the geometry part is built here (pure
+integer arithmetic, testable on a CPU), the pointer part (``X``, ``Y``, ``arena`` …) is filled in by the caller right
+before the launch.  :func:`emulate` executes a plan with the *same* index formulas as the CUDA kernel (k → (tap, channel)
+decode, live-tap list, pixel table, padded-channel remap, output mapping) on NumPy arrays, so the formulas are checked
+against ``torch.nn.functional.conv2d`` and its autograd gradients without a GPU (``tests/test_conv_plan.py``); on the GPU
+the kernel is then compared with this emulator's oracle (``tests/test_conv_gpu.py``).
+
+Reference hot loop replaced: ``murmura/core/node.py:59-109`` (forward / backward / SGD step through autograd).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+MODE_F, MODE_D, MODE_W = 0, 1, 2
+BM, BK = 128, 32
+
+
+def ceil4(x: int) -> int:
+    return (x + 3) // 4 * 4
+
+
+@dataclass(frozen=True)
+class ConvGeom:
+    """One conv (or linear: 1×1 map, 1×1 kernel) layer at a fixed batch size.  Activations are NHWC with ``Cin_pad`` /
+    ``Cout_pad`` floats per pixel (multiples of 4, zero padded); weights are (Cout, KH, KW, Cin) as stored in the arena."""
+    B: int
+    IH: int
+    IW: int
+    Cin: int
+    Cout: int
+    KH: int = 1
+    KW: int = 1
+    stride: int = 1
+    pad: int = 0
+    Cin_pad: int = 0
+    Cout_pad: int = 0
+
+    def __post_init__(self):
+        object.__setattr__(self, "Cin_pad", self.Cin_pad or ceil4(self.Cin))
+        object.__setattr__(self, "Cout_pad", self.Cout_pad or ceil4(self.Cout))
+        assert self.Cin_pad % 4 == 0 and self.Cout_pad % 4 == 0 and self.Cin_pad >= self.Cin and self.Cout_pad >= self.Cout
+        assert self.IH <= 256 and self.IW <= 256 and self.B < 32768, "pixel table packs (b, y, x) as 15/8/8 bits"
+
+    @property
+    def OH(self) -> int:
+        return (self.IH + 2 * self.pad - self.KH) // self.stride + 1
+
+    @property
+    def OW(self) -> int:
+        return (self.IW + 2 * self.pad - self.KW) // self.stride + 1
+
+    @property
+    def wrow(self) -> int:
+        return self.KH * self.KW * self.Cin
+
+    def live_taps(self) -> List[int]:
+        """Taps (kh·KW + kw) that land on at least one real input pixel for some output pixel."""
+        rows = [kh for kh in range(self.KH) if any(0 <= oh * self.stride + kh - self.pad < self.IH for oh in range(self.OH))]
+        cols = [kw for kw in range(self.KW) if any(0 <= ow * self.stride + kw - self.pad < self.IW for ow in range(self.OW))]
+        return [kh * self.KW + kw for kh in rows for kw in cols]
+
+
+def linear_geom(B: int, K: int, N: int) -> ConvGeom:
+    return ConvGeom(B=B, IH=1, IW=1, Cin=K, Cout=N)
+
+
+def pixel_table(B: int, H: int, W: int) -> np.ndarray:
+    """``b << 16 | y << 8 | x`` for every pixel of a [B, H, W] plane, row-major."""
+    b, y, x = np.meshgrid(np.arange(B), np.arange(H), np.arange(W), indexing="ij")
+    return ((b << 16) | (y << 8) | x).astype(np.int32).ravel()
+
+
+def choose_splitk(ctas: int, kb_total: int, target_ctas: int = 148, min_kb: int = 4) -> int:
+    """Split-K so that a launch has ≈ ``target_ctas`` CTAs while every slice keeps ≥ ``min_kb`` k-blocks."""
+    if ctas >= target_ctas or kb_total <= min_kb:
+        return 1
+    return max(1, min((target_ctas + ctas - 1) // ctas, kb_total // min_kb))
+
+
+def _bn_tile(n: int) -> int:
+    return 128 if n > 64 else 64
+
+
+def plan_fprop(g: ConvGeom, *, aligned_weights: bool = True) -> Dict:
+    taps = g.live_taps()
+    K = len(taps) * g.Cin_pad
+    vec = 4 if (aligned_weights and g.Cin == g.Cin_pad and g.wrow % 4 == 0) else 1
+    return {"mode": MODE_F, "M": g.B * g.OH * g.OW, "N": g.Cout, "K": K, "SH": g.IH, "SW": g.IW, "C": g.Cin_pad,
+            "lds": g.Cin_pad, "KW": g.KW, "stride": g.stride, "pad": g.pad, "taps": taps, "Cw_real": g.Cin, "Ck_real": g.Cin_pad,
+            "wrow": g.wrow, "ldy": g.Cout_pad, "vecB": vec, "BN": _bn_tile(g.Cout), "ptab_shape": (g.B, g.OH, g.OW)}
+
+
+def plan_dgrad(g: ConvGeom) -> Dict:
+    assert g.Cin == g.Cin_pad, "dgrad is never needed for (channel-padded) first layers"
+    taps = g.live_taps()
+    return {"mode": MODE_D, "M": g.B * g.IH * g.IW, "N": g.Cin, "K": len(taps) * g.Cout_pad, "SH": g.OH, "SW": g.OW,
+            "C": g.Cout_pad, "lds": g.Cout_pad, "KW": g.KW, "stride": g.stride, "pad": g.pad, "taps": taps, "Cw_real": g.Cin,
+            "Ck_real": g.Cout, "wrow": g.wrow, "ldy": g.Cin_pad, "vecB": 4, "BN": _bn_tile(g.Cin), "ptab_shape": (g.B, g.IH, g.IW)}
+
+
+def plan_wgrad(g: ConvGeom, *, bias: bool) -> Dict:
+    taps = g.live_taps()
+    return {"mode": MODE_W, "M": len(taps) * g.Cin_pad, "N": g.Cout, "K": g.B * g.OH * g.OW, "SH": g.IH, "SW": g.IW,
+            "C": g.Cin_pad, "lds": g.Cin_pad, "KW": g.KW, "stride": g.stride, "pad": g.pad, "taps": taps, "Cw_real": g.Cin,
+            "Ck_real": g.Cin_pad, "wrow": g.wrow, "ldy": g.Cout_pad, "vecB": 4, "ones_row": 1 if bias else 0, "BN": _bn_tile(g.Cout),
+            "ptab_shape": (g.B, g.OH, g.OW)}
+
+
+def grid_of(plan: Dict, G: int = 1) -> tuple:
+    m_ext = plan["M"] + (1 if plan["mode"] == MODE_W and plan.get("ones_row") else 0)
+    return ((m_ext + BM - 1) // BM, (plan["N"] + plan["BN"] - 1) // plan["BN"], G)
+
+
+def kb_total(plan: Dict) -> int:
+    return (plan["K"] + BK - 1) // BK
+
+
+# =====================================================================================================================
+# NumPy emulator (same formulas as conv_tcgen05.cu; no tiling, no swizzle)
+# =====================================================================================================================
+def _gather_pixel(plan: Dict, pk: np.ndarray, kh: int, kw: int, dgrad: bool):
+    b, y, x = pk >> 16, (pk >> 8) & 255, pk & 255
+    s, pad = plan["stride"], plan["pad"]
+    if dgrad:
+        ty, tx = y + pad - kh, x + pad - kw
+        ok = (ty >= 0) & (tx >= 0) & (ty % s == 0) & (tx % s == 0)
+        sy, sx = ty // s, tx // s
+    else:
+        sy, sx = y * s + kh - pad, x * s + kw - pad
+        ok = (sy >= 0) & (sx >= 0)
+    ok &= (sy < plan["SH"]) & (sx < plan["SW"])
+    pix = (b * plan["SH"] + sy) * plan["SW"] + sx
+    return ok, np.where(ok, pix, 0)
+
+
+def _im2col(plan: Dict, X: np.ndarray, ptab: np.ndarray, nrows: int, dgrad: bool) -> np.ndarray:
+    """A[r, k] of modes F / D (rows = ptab entries, k = (live tap, channel))."""
+    C, K = plan["C"], plan["K"]
+    A = np.zeros((nrows, K), dtype=np.float64)
+    for lt, tap in enumerate(plan["taps"]):
+        kh, kw = divmod(tap, plan["KW"])
+        ok, pix = _gather_pixel(plan, ptab[:nrows], kh, kw, dgrad)
+        cols = X[(pix[:, None] * plan["lds"] + np.arange(C)[None, :])]
+        A[:, lt * C:(lt + 1) * C] = np.where(ok[:, None], cols, 0.0)
+    return A
+
+
+def emulate(plan: Dict, X: np.ndarray, Y: np.ndarray, row: np.ndarray, R: Optional[np.ndarray] = None) -> None:
+    """Run one group of ``plan``: ``X`` / ``Y`` / ``R`` are flat activation buffers, ``row`` the node's flat arena row.
+    F, D write (or accumulate into) ``Y``; W updates ``row`` in place."""
+    mode, M, N, K, C = plan["mode"], plan["M"], plan["N"], plan["K"], plan["C"]
+    taps, Cw, wrow, ldy, w_off = plan["taps"], plan["Cw_real"], plan["wrow"], plan["ldy"], plan["w_off"]
+    alpha = float(plan.get("alpha", 1.0))
+    ptab = pixel_table(*plan["ptab_shape"])
+    if mode in (MODE_F, MODE_D):
+        A = _im2col(plan, X, ptab, M, dgrad=(mode == MODE_D))
+        Bm = np.zeros((N, K), dtype=np.float64)
+        for lt, tap in enumerate(taps):
+            if mode == MODE_F:
+                for cc in range(min(C, Cw)):
+                    Bm[:, lt * C + cc] = row[w_off + np.arange(N) * wrow + tap * Cw + cc]
+            else:
+                for co in range(min(C, plan["Ck_real"])):
+                    Bm[:, lt * C + co] = row[w_off + co * wrow + tap * Cw + np.arange(N)]
+        out = alpha * (A @ Bm.T)
+        if plan.get("bias_off", -1) >= 0:
+            out = out + row[plan["bias_off"] + np.arange(N)][None, :]
+        if plan.get("bn_mean_off", -1) >= 0:
+            mean, var = row[plan["bn_mean_off"] + np.arange(N)], row[plan["bn_var_off"] + np.arange(N)]
+            gam = row[plan["bn_gamma_off"] + np.arange(N)] if plan.get("bn_gamma_off", -1) >= 0 else 1.0
+            bet = row[plan["bn_beta_off"] + np.arange(N)] if plan.get("bn_beta_off", -1) >= 0 else 0.0
+            out = (out - mean) / np.sqrt(var + plan.get("eps", 1e-5)) * gam + bet
+        idx = (np.arange(M)[:, None] * ldy + np.arange(N)[None, :])
+        if R is not None:
+            out = np.where(R[idx] > 0, out, 0.0) if plan.get("rmode", 1) == 2 else out + R[idx]
+        if plan.get("relu"):
+            out = np.maximum(out, 0.0)
+        elif plan.get("act") == 2:
+            out = np.where(out > 20, out, np.log1p(np.exp(np.minimum(out, 20)))) + 1.0
+        if plan.get("accumulate"):
+            Y[idx] += out.astype(Y.dtype)
+        else:
+            Y[idx] = out.astype(Y.dtype)
+        return
+    # ---- W: rows m = (live tap, channel), reduction over output pixels ----
+    P = K
+    Mreal = len(taps) * C
+    A = np.zeros((Mreal, P), dtype=np.float64)
+    for lt, tap in enumerate(taps):
+        kh, kw = divmod(tap, plan["KW"])
+        ok, pix = _gather_pixel(plan, ptab[:P], kh, kw, dgrad=False)
+        cols = X[(pix[:, None] * plan["lds"] + np.arange(C)[None, :])]
+        A[lt * C:(lt + 1) * C, :] = np.where(ok[:, None], cols, 0.0).T
+    dY = Y[(np.arange(P)[:, None] * ldy + np.arange(N)[None, :])].astype(np.float64)
+    D = alpha * (A @ dY)                                        # [Mreal, N]
+    for lt, tap in enumerate(taps):
+        for cc in range(min(C, Cw)):
+            row[w_off + np.arange(N) * wrow + tap * Cw + cc] += D[lt * C + cc].astype(row.dtype)
+    if plan.get("ones_row") and plan.get("bias_off", -1) >= 0:
+        row[plan["bias_off"] + np.arange(N)] += (alpha * dY.sum(axis=0)).astype(row.dtype)

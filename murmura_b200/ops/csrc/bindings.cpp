@@ -72,6 +72,17 @@ void dmtt_update(Tensor adj, Tensor claims, Tensor collab, Tensor received, Tens
                  Tensor alpha, Tensor beta, Tensor next_collab, Tensor q_out, double rho, double lam, double w_d, double w_x,
                  double tau_U, double eta, double l1, double l2, double l3, int64_t B, Tensor gids);
 
+// conv_tcgen05.cu / layers.cu (plans are dicts built by murmura_b200/ops/conv_plan.py and parallel/fused_trainer.py)
+int64_t conv_gemm(py::dict plan);
+void gather_grouped(py::dict d);
+void bn_fwd_grouped(py::dict d);
+void bn_bwd_grouped(py::dict d);
+void maxpool_fwd_grouped(py::dict d);
+void maxpool_bwd_grouped(py::dict d);
+void avgpool_grouped(py::dict d);
+void dropout_grouped(py::dict d);
+void loss_grouped(py::dict d);
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "murmura_b200 sm_100a kernels";
     bind_arena(m);
@@ -112,4 +123,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("mobility_adjacency", &mobility_adjacency);
     m.def("liar_claims", &liar_claims);
     m.def("dmtt_update", &dmtt_update);
+    m.def("conv_gemm", &conv_gemm, "grouped implicit-GEMM conv / linear layer on tcgen05 (fprop, dgrad, wgrad + SGD)");
+    m.def("gather_grouped", &gather_grouped);
+    m.def("bn_fwd_grouped", &bn_fwd_grouped);
+    m.def("bn_bwd_grouped", &bn_bwd_grouped);
+    m.def("maxpool_fwd_grouped", &maxpool_fwd_grouped);
+    m.def("maxpool_bwd_grouped", &maxpool_bwd_grouped);
+    m.def("avgpool_grouped", &avgpool_grouped);
+    m.def("dropout_grouped", &dropout_grouped);
+    m.def("loss_grouped", &loss_grouped);
 }
