@@ -60,6 +60,7 @@ struct ConvGemmParams {
     int ldy;
     float alpha, eps;
     int relu, act, accumulate, vecB, ones_row;
+    int mn_swap;                                // debug: swap the LBO / SBO roles of MN-major descriptors (ops/selfcheck.py probes it)
     unsigned char taps[64];
 };
 
@@ -351,9 +352,12 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
             const uint32_t sa = smem0 + s * STAGE, sb = sa + kCgABytes;
 #pragma unroll
             for (int k = 0; k < kCgBK / 8; ++k) {
-                const uint64_t ad = A_MN ? umma_desc_sw128(sa + k * (kCgBM / 32) * 1024, 1024, (kCgBM / 32) * 1024)
+                // MN-major: atoms along M/N are 1 KiB apart (LBO), the next 8 k's are (rows/32) KiB apart (SBO)
+                const uint32_t a_lbo = p.mn_swap ? (kCgBM / 32) * 1024 : 1024, a_sbo = p.mn_swap ? 1024 : (kCgBM / 32) * 1024;
+                const uint32_t b_lbo = p.mn_swap ? (BN / 32) * 1024 : 1024, b_sbo = p.mn_swap ? 1024 : (BN / 32) * 1024;
+                const uint64_t ad = A_MN ? umma_desc_sw128(sa + k * (kCgBM / 32) * 1024, a_lbo, a_sbo)
                                          : umma_desc_sw128(sa + k * 32, 0, 1024);
-                const uint64_t bd = B_MN ? umma_desc_sw128(sb + k * (BN / 32) * 1024, 1024, (BN / 32) * 1024)
+                const uint64_t bd = B_MN ? umma_desc_sw128(sb + k * (BN / 32) * 1024, b_lbo, b_sbo)
                                          : umma_desc_sw128(sb + k * 32, 0, 1024);
                 umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
@@ -413,7 +417,7 @@ int64_t conv_gemm(py::dict d) {
     p.ldy = d["ldy"].cast<int>();
     p.alpha = dget<float>(d, "alpha", 1.f); p.eps = dget<float>(d, "eps", 1e-5f);
     p.relu = dget<int>(d, "relu", 0); p.act = dget<int>(d, "act", 0); p.accumulate = dget<int>(d, "accumulate", 0);
-    p.vecB = dget<int>(d, "vecB", 4); p.ones_row = dget<int>(d, "ones_row", 0);
+    p.vecB = dget<int>(d, "vecB", 4); p.ones_row = dget<int>(d, "ones_row", 0); p.mn_swap = dget<int>(d, "mn_swap", 0);
     auto taps = d["taps"].cast<std::vector<int>>();
     TORCH_CHECK(!taps.empty() && taps.size() <= 64, "conv_gemm: 1..64 live taps");
     p.ntaps = (int)taps.size();

@@ -395,6 +395,10 @@ class LossOp:
 # =====================================================================================================================
 # program builder
 # =====================================================================================================================
+class _Unsupported(Exception):
+    pass
+
+
 class _Builder:
     def __init__(self, tr: "FusedTrainer", B: int):
         self.tr, self.B, self.ops = tr, B, []
@@ -417,6 +421,8 @@ class _Builder:
         else:
             g = cp.ConvGeom(B=self.B, IH=1, IW=1, Cin=m.in_features, Cout=m.out_features, Cin_pad=x.ld)
         assert x.ld >= g.Cin and (first or x.ld == g.Cin), f"{prefix}: input buffer has {x.ld} floats per pixel for {g.Cin} channels"
+        if not first and (self.off(prefix + ".weight") % 4 or g.wrow % 4):
+            raise _Unsupported(f"{prefix}: weights are not 16-byte aligned in the arena row")
         y = self.buf(prefix + ".out", self.B * g.OH * g.OW, g.Cout)
         bias = self.off(prefix + ".bias") if m.bias is not None else -1
         self.ops.append(ConvOp(prefix, x, y, g, self.off(prefix + ".weight"), bias, relu=relu, act=act, first=first))
@@ -620,7 +626,10 @@ class FusedTrainer:
         self.logits: Optional[Buf] = None
         self.xb: Optional[Buf] = None
         self.npix = self.Csrc = self.Cdst = 0
-        self.supported = build_program(self, model, self.eb, sample_shape)
+        try:
+            self.supported = build_program(self, model, self.eb, sample_shape)
+        except (_Unsupported, AssertionError) as exc:
+            self.supported, self.unsupported_reason = False, str(exc)
         if self.supported and evidential != self.evidential_head:
             self.supported = False                      # criterion / head mismatch: leave it to the autograd path
         if not self.supported:
