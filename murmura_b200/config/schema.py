@@ -121,6 +121,11 @@ class B200Config(BaseModel):
         default="balanced", description="virtual-node → GPU map: balanced = longest-shard-first onto the least-loaded GPU")
     unroll_round: bool = Field(default=True, description="capture ALL local steps of a node's round (epochs x batches) in one CUDA "
                                "graph instead of one graph per step (fewer graph launches; matters for tiny models)")
+    fused_train: Union[bool, Literal["auto"]] = Field(
+        default="auto", description="train all nodes of a GPU with the fused tcgen05 program (parallel/fused_trainer.py: grouped implicit-GEMM "
+                                    "conv / linear kernels with the SGD step in the wgrad epilogue, one CUDA graph per round); auto = whenever the "
+                                    "model family, loss and layout are supported, otherwise the per-node autograd graphs")
+    fused_side_stream: bool = Field(default=True, description="fused_train: weight-gradient launches on a parallel graph branch")
     batched_mlp_train: bool = Field(default=False, description="train all MLP-family nodes of a GPU in one batched step (strided-batched GEMMs "
                                     "over arena-row views, masked per-node BatchNorm/SGD); opt-in, falls back to per-node graphs")
     grouped_mlp: bool = Field(default=True, description="score foreign MLP weights (UBAR stage 2 / EvidentialTrust / DMTT) with the "

@@ -12,8 +12,9 @@
 //
 // Activations are NHWC fp32, weights (Cout, KH, KW, Cin) fp32 — the physical layout of the arena.  Operand tiles are
 // gathered by cp.async (16 B, zero-fill for padding / out-of-range taps) straight into 128-byte-swizzled shared memory:
-// K-major tiles for im2col rows and fprop weights, MN-major tiles for dgrad weights and both wgrad operands (their
-// reduction index is the slow axis in memory, so no transposition pass is ever needed).  One elected thread issues
+// K-major tiles (SWIZZLE_128B) for im2col rows and fprop weights, MN-major tiles (SWIZZLE_128B_BASE32B, the tf32 transposing
+// layout) for dgrad weights and both wgrad operands — their reduction index is the slow axis in memory, so no
+// transposition pass is ever needed.  One elected thread issues
 // `tcgen05.mma.kind::tf32` (fp32 operands consumed in place, fp32 accumulation in TMEM); a 4-stage mbarrier ring
 // decouples the 4 loader warps from the MMA warp; the loader warps then run the epilogue out of TMEM (`tcgen05.ld`).
 // Only taps that touch at least one real pixel are visited ("live taps": a 3×3 conv on a 1×1 map is a 1×1 conv).
@@ -140,10 +141,12 @@ __device__ __forceinline__ void load_b_weights_k(const ConvGemmParams& p, const 
     }
 }
 
-// MN-major tile [4 k-groups][ROWS/32 atoms][8 k-rows][128 B]: address of chunk `c` (4 consecutive rows) of k-row `j`.
+// MN-major tile [8 k-groups of 4][ROWS/32 atoms][4 k-rows][128 B] (SWIZZLE_128B_BASE32B): address of the 16-byte chunk `c`
+// (4 consecutive M/N rows) of k-row `j` — the 32-byte chunk index is XOR-ed with (j % 4).
 template <int ROWS>
 __device__ __forceinline__ uint32_t mn_chunk_addr(uint32_t base, int j, int c) {
-    return base + (((j >> 3) * (ROWS / 32) + (c >> 3)) << 10) + ((j & 7) << 7) + ((((c & 7) ^ (j & 7))) << 4);
+    const int r = j & 3, c16 = c & 7;
+    return base + (((j >> 2) * (ROWS / 32) + (c >> 3)) << 9) + (r << 7) + ((((c16 >> 1) ^ r)) << 5) + ((c16 & 1) << 4);
 }
 
 // ---- operand B of mode D, MN-major: W[co][tap][ci] with k = (tap, co), rows n = ci ------------------------------------------
@@ -352,12 +355,13 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
             const uint32_t sa = smem0 + s * STAGE, sb = sa + kCgABytes;
 #pragma unroll
             for (int k = 0; k < kCgBK / 8; ++k) {
-                // MN-major: atoms along M/N are 1 KiB apart (LBO), the next 8 k's are (rows/32) KiB apart (SBO)
-                const uint32_t a_lbo = p.mn_swap ? (kCgBM / 32) * 1024 : 1024, a_sbo = p.mn_swap ? 1024 : (kCgBM / 32) * 1024;
-                const uint32_t b_lbo = p.mn_swap ? (BN / 32) * 1024 : 1024, b_sbo = p.mn_swap ? 1024 : (BN / 32) * 1024;
-                const uint64_t ad = A_MN ? umma_desc_sw128(sa + k * (kCgBM / 32) * 1024, a_lbo, a_sbo)
+                // MN-major (BASE32B): atoms along M/N are 512 B apart (LBO), the next 4 k's are (rows/32)·512 B apart (SBO);
+                // one UMMA_K = 8 step = two k-groups
+                const uint32_t a_lbo = p.mn_swap ? (kCgBM / 32) * 512 : 512, a_sbo = p.mn_swap ? 512 : (kCgBM / 32) * 512;
+                const uint32_t b_lbo = p.mn_swap ? (BN / 32) * 512 : 512, b_sbo = p.mn_swap ? 512 : (BN / 32) * 512;
+                const uint64_t ad = A_MN ? umma_desc(sa + k * (kCgBM / 32) * 1024, a_lbo, a_sbo, kLayoutSw128Base32)
                                          : umma_desc_sw128(sa + k * 32, 0, 1024);
-                const uint64_t bd = B_MN ? umma_desc_sw128(sb + k * (BN / 32) * 1024, b_lbo, b_sbo)
+                const uint64_t bd = B_MN ? umma_desc(sb + k * (BN / 32) * 1024, b_lbo, b_sbo, kLayoutSw128Base32)
                                          : umma_desc_sw128(sb + k * 32, 0, 1024);
                 umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }

@@ -409,20 +409,20 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* dy, long 
 }
 
 // ---- stand-alone dropout (models that apply it after a plain ReLU) ------------------------------------------------------
-__global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* y, const float* mask, long long gs, long long n4, const int* gmap,
+__global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* y, const float* mask, long long x_gs, long long y_gs, long long m_gs, long long n4, const int* gmap,
                                                       const long long* rng_step, unsigned long long seed, int layer_id, float p_drop) {
     const int g = blockIdx.y;
     const int slot = gmap ? gmap[g] : g;
     const uint64_t stream = ((uint64_t)(*rng_step) << 24) ^ ((uint64_t)layer_id << 12) ^ (uint64_t)slot;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 v = reinterpret_cast<const float4*>(x + (long long)g * gs)[i];
+        float4 v = reinterpret_cast<const float4*>(x + (long long)g * x_gs)[i];
         const float4 k = dropout_scale4(seed, stream, (uint64_t)i, p_drop);
         v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
         if (mask) {                                            // backward through a ReLU fused into the producer of the dropped tensor
-            const float4 m = reinterpret_cast<const float4*>(mask + (long long)g * gs)[i];
+            const float4 m = reinterpret_cast<const float4*>(mask + (long long)g * m_gs)[i];
             v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
         }
-        reinterpret_cast<float4*>(y + (long long)g * gs)[i] = v;
+        reinterpret_cast<float4*>(y + (long long)g * y_gs)[i] = v;
     }
 }
 
@@ -444,7 +444,7 @@ __device__ __forceinline__ float gl_trigamma(float x) {
 
 // softmax cross-entropy, mean over the batch: grad[b][c] = (softmax − onehot)/B, padding columns [C, ld) are written as 0
 __global__ void __launch_bounds__(256) ce_loss_grouped_kernel(const float* logits, long long gs, const long long* targets, long long t_gs,
-                                                              float* grad, float* loss_acc, const int* gmap, int B, int C, int ld) {
+                                                              float* grad, long long grad_gs, float* loss_acc, const int* gmap, int B, int C, int ld) {
     __shared__ float wsum[8];
     const int g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) ce_loss_grouped_kernel(const float* logit
     float local = 0.f;
     for (int r = warp; r < B; r += 8) {
         const float* z = logits + (long long)g * gs + (long long)r * ld;
-        float* gr = grad + (long long)g * gs + (long long)r * ld;
+        float* gr = grad + (long long)g * grad_gs + (long long)r * ld;
         const int t = (int)targets[(long long)g * t_gs + r];
         float mx = -INFINITY;
         for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) ce_loss_grouped_kernel(const float* logit
 // evidential loss on α = softplus(z) + 1 (reference examples/wearables/models.py:89-179): grad is dL/dz = dL/dα · σ(z),
 // σ(z) = 1 − exp(−(α − 1)); λ is read from the device (annealing schedule without re-capturing the graph)
 __global__ void __launch_bounds__(256) evidential_loss_grouped_kernel(const float* alpha, long long gs, const long long* targets, long long t_gs,
-                                                                      float* grad, float* loss_acc, const int* gmap, const float* lam_ptr,
+                                                                      float* grad, long long grad_gs, float* loss_acc, const int* gmap, const float* lam_ptr,
                                                                       int B, int C, int ld) {
     __shared__ float wsum[8];
     const int g = blockIdx.x;
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) evidential_loss_grouped_kernel(const floa
     float local = 0.f;
     for (int r = warp; r < B; r += 8) {
         const float* a = alpha + (long long)g * gs + (long long)r * ld;
-        float* gr = grad + (long long)g * gs + (long long)r * ld;
+        float* gr = grad + (long long)g * grad_gs + (long long)r * ld;
         const int t = (int)targets[(long long)g * t_gs + r];
         float S = 0.f;
         for (int c = lane; c < C; c += 32) S += a[c];
@@ -658,7 +658,7 @@ void dropout_grouped(py::dict d) {
     const long long n = d["n"].cast<int64_t>();
     TORCH_CHECK(n % 4 == 0);
     dim3 grid(gs_blocks(n / 4, G), G);
-    mb::dropout_kernel<<<grid, 256, 0, lstream()>>>(lptr<const float>(d, "x"), lptr<float>(d, "y"), lptr<const float>(d, "mask"), d["gs"].cast<int64_t>(), n / 4, lptr<const int>(d, "gmap"),
+    mb::dropout_kernel<<<grid, 256, 0, lstream()>>>(lptr<const float>(d, "x"), lptr<float>(d, "y"), lptr<const float>(d, "mask"), d["x_gs"].cast<int64_t>(), d["y_gs"].cast<int64_t>(), lget<int64_t>(d, "m_gs", 0), n / 4, lptr<const int>(d, "gmap"),
                                                     lptr<const long long>(d, "rng_step"), (unsigned long long)lget<int64_t>(d, "seed", 0),
                                                     lget<int>(d, "layer_id", 0), d["p_drop"].cast<float>());
     C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -670,9 +670,9 @@ void loss_grouped(py::dict d) {
     TORCH_CHECK(B > 0 && C > 0 && ld >= C);
     if (evidential)
         mb::evidential_loss_grouped_kernel<<<G, 256, 0, lstream()>>>(lptr<const float>(d, "out"), d["gs"].cast<int64_t>(), lptr<const long long>(d, "targets"),
-            d["t_gs"].cast<int64_t>(), lptr<float>(d, "grad"), lptr<float>(d, "loss_acc"), lptr<const int>(d, "gmap"), lptr<const float>(d, "lam"), B, C, ld);
+            d["t_gs"].cast<int64_t>(), lptr<float>(d, "grad"), lget<int64_t>(d, "grad_gs", d["gs"].cast<int64_t>()), lptr<float>(d, "loss_acc"), lptr<const int>(d, "gmap"), lptr<const float>(d, "lam"), B, C, ld);
     else
         mb::ce_loss_grouped_kernel<<<G, 256, 0, lstream()>>>(lptr<const float>(d, "out"), d["gs"].cast<int64_t>(), lptr<const long long>(d, "targets"),
-            d["t_gs"].cast<int64_t>(), lptr<float>(d, "grad"), lptr<float>(d, "loss_acc"), lptr<const int>(d, "gmap"), B, C, ld);
+            d["t_gs"].cast<int64_t>(), lptr<float>(d, "grad"), lget<int64_t>(d, "grad_gs", d["gs"].cast<int64_t>()), lptr<float>(d, "loss_acc"), lptr<const int>(d, "gmap"), B, C, ld);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

@@ -84,18 +84,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptors (sm_100 version 1), 128-byte swizzle.
-//   K-major operand  : rows of 32 fp32 (128 B), 8-row groups `sbo` bytes apart; a UMMA_K = 8 step advances the start by 32 B.
-//   MN-major operand : rows are k indices holding 32 consecutive M/N elements (128 B); 8 k-rows form one 1 KiB atom;
-//                      atoms along M/N are `lbo` bytes apart, the next 8 k's are `sbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptors (sm_100 version 1).
+//   K-major operand, SWIZZLE_128B (layout 2): rows of 32 fp32 (128 B), 16-byte chunks XOR-ed with (row % 8), 8-row groups `sbo`
+//     bytes apart; a UMMA_K = 8 step advances the start address by 32 B.
+//   MN-major fp32 operand, SWIZZLE_128B_BASE32B (layout 1, the only legal choice for tf32): a row is ONE k index holding 32
+//     consecutive M/N elements (128 B) whose 32-byte chunks are XOR-ed with (k % 4); 4 k-rows form a 512-byte atom; atoms
+//     along M/N are `lbo` bytes apart, the next 4 k's are `sbo` bytes apart (a UMMA_K = 8 step spans two k-groups).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return umma_desc(smem_addr, lbo_bytes, sbo_bytes, kLayoutSw128);
 }
 // kind::tf32, fp32 accumulate; a_mn / b_mn select MN-major operands (bits 15 / 16).
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn, int b_mn) {

@@ -185,16 +185,24 @@ def bench_case(h: Harness, case: Tuple, mode: str, G: int, iters: int = 30) -> D
     plan["splitk"] = split
     if split > 1 and mode != "W":
         plan["accumulate"] = 1
-    for _ in range(5):
+    for _ in range(3):
         ctas = h.launch(plan, G, src, dst, arena)
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
-    ev[0].record()
-    for i in range(iters):
-        h.launch(plan, G, src, dst, arena)
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    ts = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(iters))
+    # the Python launch path costs more than these kernels run: time a CUDA graph of `reps` back-to-back launches
+    reps = 20
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(reps):
+            h.launch(plan, G, src, dst, arena)
+    graph.replay(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters // 3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); graph.replay(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / reps)
+    ts.sort()
     flops = 2.0 * G * B * g.OH * g.OW * Cout * len(plan["taps"]) * Cin
     us = ts[len(ts) // 2]
     return {"case": name, "mode": mode, "G": G, "us": round(us, 2), "us_min": round(ts[0], 2), "ctas": ctas, "splitk": split,

@@ -519,6 +519,11 @@ class B200Network:
 
     def _prepare_training(self, epochs: int, lr: float) -> None:
         key = (epochs, lr)
+        cache = self.__dict__.setdefault("_fused_cache", {})
+        if epochs not in cache:
+            cache[epochs] = self._fused_setup(epochs)
+        if cache[epochs] is not None:
+            return                                              # the fused program replaces the per-node autograd graphs
         for vn in self.nodes:
             if vn.byzantine or vn.nb == 0:
                 continue
@@ -572,6 +577,8 @@ class B200Network:
         self._fused_evidential = self.evidential and isinstance(self.criterion, EvidentialLoss)
         if isinstance(self.criterion, EvidentialLoss):
             self.lam_t.fill_(self.criterion.anneal(self.round_idx))
+        if self._fused_training(epochs, lr):
+            return
         if self.opt.batched_mlp_train and self._batched_training(epochs, lr):
             return
         self._fork()
@@ -598,6 +605,61 @@ class B200Network:
                         self._train_step(vn, lr)
                 self.kernel_launches += epochs * vn.nb * vn.launches_per_step
         self._join()
+
+    # ---- fused program: every layer of every node of this GPU in ONE launch (parallel/fused_trainer.py) -------------------------
+    def _fused_setup(self, epochs: int):
+        """Build the fused trainer for this GPU's nodes; ``None`` when the model family / loss / layout is not supported."""
+        from murmura_b200.models.mlp import EvidentialLoss
+        from murmura_b200.parallel.fused_trainer import FusedTrainer
+        mode = self.opt.fused_train
+        if not mode or not self.nodes or self.opt.compute_dtype == "bf16" or not self.opt.cuda_graphs:
+            return None
+        if self.evidential and not isinstance(self.criterion, EvidentialLoss):
+            return None
+        if not self.evidential and not self._plain_ce():
+            return None
+        live = [vn for vn in self.nodes if not vn.byzantine and vn.nb > 0]
+        if not live:
+            return None
+        if len({vn.eb for vn in live}) != 1:
+            return None                                         # mixed effective batch sizes (a shard smaller than the batch)
+        first = self.nodes[0]
+        if first.X.dim() == 4 and not first.nhwc:
+            return None
+        shape = (first.X.shape[3], first.X.shape[1], first.X.shape[2]) if first.X.dim() == 4 else tuple(first.X.shape[1:])
+        steps = [0 if (vn.byzantine or vn.nb == 0) else epochs * vn.nb for vn in self.nodes]
+        tr = FusedTrainer(first.model, self.layout, self.live, self.ints if self.layout.Pi else None, [(vn.X, vn.y) for vn in self.nodes],
+                          steps, live[0].eb, shape, evidential=self.evidential, seed=int(self.cfg.experiment.seed),
+                          side_stream=bool(self.opt.fused_side_stream))
+        if not tr.supported:
+            if mode is True and self.is_primary:
+                print(f"[b200] fused_train unavailable for this model ({getattr(tr, 'unsupported_reason', 'unsupported family')}); "
+                      "using per-node autograd graphs")
+            return None
+        tr.lam_t = self.lam_t                                    # annealing coefficient is read on the device
+        return tr
+
+    def _fused_training(self, epochs: int, lr: float) -> bool:
+        cache = self.__dict__.setdefault("_fused_cache", {})
+        if epochs not in cache:
+            cache[epochs] = self._fused_setup(epochs)
+        tr = cache[epochs]
+        if tr is None:
+            return False
+        if self._host_shards:                                    # end-to-end mode: this round's inputs come from pinned host memory
+            for i, vn in enumerate(self.nodes):
+                vn.X.copy_(self._host_shards[i][0], non_blocking=True)
+                vn.y.copy_(self._host_shards[i][1], non_blocking=True)
+        tr.loss_acc.zero_()
+        before = tr.be.launches
+        tr.run_round(epochs, lr)
+        if tr.be.launches > before:                              # the round was (re)captured: remember its launch count
+            tr.launches_in_graph = (tr.be.launches - before) * tr.max_steps // (tr.max_steps + 1) if tr.max_steps else 0
+        self.kernel_launches += getattr(tr, "launches_in_graph", 0)
+        for vn in self.nodes:
+            vn.loss_sum = tr.loss_acc[vn.slot]
+        self.fused = tr
+        return True
 
     # ---- K8b: all MLP nodes of this GPU in one batched step (opt-in: b200.batched_mlp_train) ------------------------------
     def _batched_setup(self, epochs: int, lr: float):
@@ -1506,6 +1568,7 @@ class B200Network:
             vn.train_graph = None; vn.eval_graph = None; vn.split_bwd = None
         self._evaluators.clear()                      # CUDA graphs / views that point into the arena must go before it does
         self.__dict__.pop("_batched_cache", None)
+        self.__dict__.pop("_fused_cache", None); self.__dict__.pop("fused", None)
         if self.world > 1:
             _dist().barrier()
         self.arena.close()

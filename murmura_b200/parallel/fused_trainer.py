@@ -227,13 +227,14 @@ class ConvOp:
     """Conv2d / Linear (+bias) (+ReLU | softplus+1) — fprop, dgrad, wgrad+SGD launches of one layer."""
 
     def __init__(self, name: str, x: Buf, y: Buf, geom: cp.ConvGeom, w_off: int, bias_off: int, relu: bool = False, act: int = 0,
-                 first: bool = False):
+                 first: bool = False, bn: Optional[Dict[str, Any]] = None, res: Optional[Buf] = None):
         self.name, self.x, self.y, self.geom, self.w_off, self.bias_off = name, x, y, geom, w_off, bias_off
         self.relu, self.act, self.first = relu, act, first
+        self.bn, self.res = bn, res                    # inference only: eval-mode BatchNorm (+residual) folded into the epilogue
         self.pf = cp.plan_fprop(geom, aligned_weights=(w_off % 4 == 0))
         self.pd = None if first else cp.plan_dgrad(geom)
         self.pw = cp.plan_wgrad(geom, bias=bias_off >= 0)
-        self.fused_out = relu or act != 0
+        self.fused_out = relu or act != 0 or bn is not None or res is not None
         self.dgrad_accumulate = False                 # decided by the backward planner
         y.relu_fused = relu
 
@@ -252,8 +253,11 @@ class ConvOp:
         p = dict(self.pf)
         split = 1 if self.fused_out else self._split(p, G, tr.target_ctas)
         p.update(w_off=self.w_off, bias_off=self.bias_off, relu=int(self.relu), act=self.act, splitk=split)
+        if self.bn is not None:
+            p.update(bn_mean_off=self.bn["running_mean"], bn_var_off=self.bn["running_var"], bn_gamma_off=self.bn["weight"],
+                     bn_beta_off=self.bn["bias"], eps=self.bn["eps"])
         assert split == 1 or self.y.pooled
-        tr.be.conv(tr, p, G, self.x, self.y)
+        tr.be.conv(tr, p, G, self.x, self.y, R=self.res, row_tab=getattr(tr, "row_tab", None))
 
     def bwd(self, tr: "FusedTrainer", G: int, lr: float) -> None:
         dy = self.y.grad
@@ -360,18 +364,18 @@ class DropoutOp:
         self.name, self.x, self.y, self.p, self.layer_id = name, x, y, p, layer_id
 
     def _d(self, tr: "FusedTrainer", G: int) -> Dict[str, Any]:
-        return dict(G=G, gs=self.x.gs, n=self.x.size, gmap=tr.gmap.data_ptr(), rng_step=tr.rng_step.data_ptr(), seed=tr.seed,
+        return dict(G=G, n=self.x.size, gmap=tr.gmap.data_ptr(), rng_step=tr.rng_step.data_ptr(), seed=tr.seed,
                     layer_id=self.layer_id, p_drop=self.p)
 
     def fwd(self, tr: "FusedTrainer", G: int) -> None:
-        assert tr.be.name == "cuda" and self.x.gs == self.y.gs
-        d = self._d(tr, G); d.update(x=self.x.ptr(), y=self.y.ptr())
+        assert tr.be.name == "cuda"
+        d = self._d(tr, G); d.update(x=self.x.ptr(), x_gs=self.x.gs, y=self.y.ptr(), y_gs=self.y.gs)
         tr.be.call("dropout_grouped", d)
 
     def bwd(self, tr: "FusedTrainer", G: int, lr: float) -> None:
-        d = self._d(tr, G); d.update(x=self.y.grad.ptr(), y=self.x.grad.ptr())
+        d = self._d(tr, G); d.update(x=self.y.grad.ptr(), x_gs=self.y.grad.gs, y=self.x.grad.ptr(), y_gs=self.x.grad.gs)
         if self.x.relu_fused:
-            d.update(mask=self.x.ptr())
+            d.update(mask=self.x.ptr(), m_gs=self.x.gs)
         tr.be.call("dropout_grouped", d)
 
 
@@ -383,9 +387,8 @@ class LossOp:
         if tr.be.name == "emu":
             return tr.be.loss(tr, G, self)
         d = dict(G=G, B=self.x.rows, C=self.x.C, ld=self.x.ld, out=self.x.ptr(), gs=self.x.gs, targets=tr.yb.data_ptr(), t_gs=tr.yb.shape[1],
-                 grad=self.x.grad.ptr(), loss_acc=tr.loss_acc.data_ptr(), gmap=tr.gmap.data_ptr(), evidential=int(self.evidential),
-                 lam=tr.lam_t.data_ptr())
-        assert self.x.grad.gs == self.x.gs
+                 grad=self.x.grad.ptr(), grad_gs=self.x.grad.gs, loss_acc=tr.loss_acc.data_ptr(), gmap=tr.gmap.data_ptr(),
+                 evidential=int(self.evidential), lam=tr.lam_t.data_ptr())
         tr.be.call("loss_grouped", d)
 
     def bwd(self, tr: "FusedTrainer", G: int, lr: float) -> None:
@@ -400,8 +403,8 @@ class _Unsupported(Exception):
 
 
 class _Builder:
-    def __init__(self, tr: "FusedTrainer", B: int):
-        self.tr, self.B, self.ops = tr, B, []
+    def __init__(self, tr: "FusedTrainer", B: int, training: bool = True):
+        self.tr, self.B, self.ops, self.training = tr, B, [], training
         self.layer_id = 0
 
     def off(self, name: str) -> int:
@@ -412,7 +415,19 @@ class _Builder:
         self.tr.bufs.append(b)
         return b
 
-    def conv(self, prefix: str, m: nn.Module, x: Buf, H: int, W: int, relu: bool = False, act: int = 0, first: bool = False) -> Tuple[Buf, int, int]:
+    def conv_bn(self, prefix: str, m: nn.Module, bn_prefix: str, bn: nn.Module, x: Buf, H: int, W: int, res: Optional[Buf], relu: bool,
+                first: bool = False, p_drop: float = 0.0) -> Tuple[Buf, int, int]:
+        """conv → BatchNorm (+residual) (+ReLU) (+dropout): two launches when training (batch statistics), ONE for inference
+        (running statistics, residual and ReLU folded into the conv epilogue; dropout is the identity)."""
+        if self.training:
+            r, OH, OW = self.conv(prefix, m, x, H, W, first=first)
+            return self.bn(bn_prefix, bn, r, res, relu=relu, p_drop=p_drop), OH, OW
+        offs = {k: self.off(f"{bn_prefix}.{k}") for k in ("weight", "bias", "running_mean", "running_var")}
+        offs["eps"] = bn.eps
+        return self.conv(prefix, m, x, H, W, relu=relu, first=first, bn=offs, res=res)
+
+    def conv(self, prefix: str, m: nn.Module, x: Buf, H: int, W: int, relu: bool = False, act: int = 0, first: bool = False,
+             bn: Optional[Dict[str, Any]] = None, res: Optional[Buf] = None) -> Tuple[Buf, int, int]:
         if isinstance(m, nn.Conv2d):
             assert m.groups == 1 and m.dilation == (1, 1) and m.kernel_size[0] == m.kernel_size[1] and m.stride[0] == m.stride[1] \
                 and m.padding[0] == m.padding[1] and m.padding_mode == "zeros"
@@ -425,7 +440,7 @@ class _Builder:
             raise _Unsupported(f"{prefix}: weights are not 16-byte aligned in the arena row")
         y = self.buf(prefix + ".out", self.B * g.OH * g.OW, g.Cout)
         bias = self.off(prefix + ".bias") if m.bias is not None else -1
-        self.ops.append(ConvOp(prefix, x, y, g, self.off(prefix + ".weight"), bias, relu=relu, act=act, first=first))
+        self.ops.append(ConvOp(prefix, x, y, g, self.off(prefix + ".weight"), bias, relu=relu, act=act, first=first, bn=bn, res=res))
         return y, g.OH, g.OW
 
     def bn(self, prefix: str, m: nn.Module, x: Buf, res: Optional[Buf], relu: bool, p_drop: float = 0.0) -> Buf:
@@ -461,12 +476,13 @@ def _pool_params(m) -> Tuple[int, int, int]:
     return k, s or k, p
 
 
-def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Sequence[int]) -> bool:
-    """Fill ``tr.ops`` / ``tr.bufs`` for ``model``; returns False when the model is not one of the supported families."""
+def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Sequence[int], training: bool = True) -> bool:
+    """Fill ``tr.ops`` / ``tr.bufs`` for ``model``; returns False when the model is not one of the supported families.
+    ``training=False`` builds the inference tape (no loss, BatchNorm folded into the conv epilogues, dropout skipped)."""
     from murmura_b200.models.cnn import CIFARCNN, FEMNISTXLarge, _TwoConvNet
     from murmura_b200.models.mlp import MLP, EvidentialMLP
     from murmura_b200.models.resnet import BasicBlock, ResNet18
-    b = _Builder(tr, B)
+    b = _Builder(tr, B, training)
     image = len(sample_shape) == 3
     if image:
         Cin, H, W = sample_shape                      # logical (C, H, W); shards are stored NHWC
@@ -483,8 +499,7 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
         return all(c.in_channels % 4 == 0 for c in convs)
 
     if isinstance(model, ResNet18) and image:
-        x, H, W = b.conv("conv1", model.conv1, x0, H, W, first=True)
-        x = b.bn("bn1", model.bn1, x, None, relu=True)
+        x, H, W = b.conv_bn("conv1", model.conv1, "bn1", model.bn1, x0, H, W, None, True, first=True)
         k, s, p = _pool_params(model.maxpool)
         x, H, W = b.maxpool("maxpool", x, H, W, 64, k, s, p)
         for li in range(1, 5):
@@ -494,12 +509,9 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
                 pre = f"layer{li}.{bi}"
                 identity = x
                 if blk.downsample is not None:
-                    d, _, _ = b.conv(pre + ".downsample.0", blk.downsample[0], x, H, W)
-                    identity = b.bn(pre + ".downsample.1", blk.downsample[1], d, None, relu=False)
-                r1, H1, W1 = b.conv(pre + ".conv1", blk.conv1, x, H, W)
-                a1 = b.bn(pre + ".bn1", blk.bn1, r1, None, relu=True)
-                r2, H, W = b.conv(pre + ".conv2", blk.conv2, a1, H1, W1)
-                x = b.bn(pre + ".bn2", blk.bn2, r2, identity, relu=True)
+                    identity, _, _ = b.conv_bn(pre + ".downsample.0", blk.downsample[0], pre + ".downsample.1", blk.downsample[1], x, H, W, None, False)
+                a1, H1, W1 = b.conv_bn(pre + ".conv1", blk.conv1, pre + ".bn1", blk.bn1, x, H, W, None, True)
+                x, H, W = b.conv_bn(pre + ".conv2", blk.conv2, pre + ".bn2", blk.bn2, a1, H1, W1, identity, True)
         C = model.fc.in_features
         if H * W > 1:
             f = b.buf("avgpool.out", B, C)
@@ -529,7 +541,7 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
             return False
         x, _, _ = b.conv("fc1", model.fc1, x, 1, 1, relu=True)
         logits, _, _ = b.conv("fc2", model.fc2, x, 1, 1)
-    elif isinstance(model, FEMNISTXLarge) and image and tr.be.name == "cuda":
+    elif isinstance(model, FEMNISTXLarge) and image and (tr.be.name == "cuda" or not training):
         x, H, W = b.conv("conv1", model.conv1, x0, H, W, relu=True, first=True)
         x, H, W = b.conv("conv2", model.conv2, x, H, W, relu=True)
         x, H, W = b.maxpool("pool1", x, H, W, 128, 2, 2, 0)
@@ -539,10 +551,11 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
             return False
         for i, fc in enumerate((model.fc1, model.fc2)):
             x, _, _ = b.conv(f"fc{i + 1}", fc, x, 1, 1, relu=True)
-            y = b.buf(f"drop{i + 1}.out", x.rows, x.C)
-            b.layer_id += 1
-            b.ops.append(DropoutOp(f"drop{i + 1}", x, y, model.dropout.p, b.layer_id))
-            x = y
+            if training:
+                y = b.buf(f"drop{i + 1}.out", x.rows, x.C)
+                b.layer_id += 1
+                b.ops.append(DropoutOp(f"drop{i + 1}", x, y, model.dropout.p, b.layer_id))
+                x = y
         logits, _, _ = b.conv("fc3", model.fc3, x, 1, 1)
     elif isinstance(model, MLP) and not image:
         mods = list(model.net.named_children())
@@ -564,7 +577,7 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
             name, m = mods[i]
             if not isinstance(m, nn.Linear) or (not first and m.in_features % 4) or m.out_features % 4:
                 return False
-            x, _, _ = b.conv(f"feature_extractor.{name}", m, x, 1, 1, first=first)
+            lin_name, lin, lin_first = name, m, first
             first = False
             j = i + 1
             bn_mod, bn_name, relu, p_drop = None, None, False, 0.0
@@ -583,7 +596,8 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
                 return False
             if p_drop > 0 and tr.be.name != "cuda":
                 p_drop = 0.0                           # the CPU emulation has no device Philox stream: tests run with p = 0
-            x = b.bn(f"feature_extractor.{bn_name}", bn_mod, x, None, relu=relu, p_drop=p_drop)
+            x, _, _ = b.conv_bn(f"feature_extractor.{lin_name}", lin, f"feature_extractor.{bn_name}", bn_mod, x, 1, 1, None, relu,
+                                first=lin_first, p_drop=p_drop)
             i = j
         if model.evidential_head.fc.in_features % 4:
             return False
@@ -591,7 +605,8 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
         tr.evidential_head = True
     else:
         return False
-    b.ops.append(LossOp(logits, tr.evidential_head))
+    if training:
+        b.ops.append(LossOp(logits, tr.evidential_head))
     tr.ops = b.ops
     tr.logits = logits
     return True
