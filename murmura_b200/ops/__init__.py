@@ -23,7 +23,7 @@ _HERE = Path(__file__).resolve().parent
 _SRC = _HERE / "csrc"
 _BUILD = _HERE / "_build"
 _NAME = "murmura_b200_ext"
-_SOURCES = ["bindings.cpp", "arena.cu", "aggregate.cu", "train.cu", "gram_tcgen05.cu", "mlp_tcgen05.cu", "dmtt.cu", "bn_train.cu", "conv_tcgen05.cu", "layers.cu"]
+_SOURCES = ["bindings.cpp", "arena.cu", "aggregate.cu", "train.cu", "gram_tcgen05.cu", "mlp_tcgen05.cu", "dmtt.cu", "bn_train.cu", "conv_tcgen05.cu", "conv_tma.cu", "layers.cu"]
 _CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--use_fast_math",
                "-std=c++17", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

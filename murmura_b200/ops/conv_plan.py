@@ -111,6 +111,75 @@ def plan_wgrad(g: ConvGeom, *, bias: bool) -> Dict:
             "ptab_shape": (g.B, g.OH, g.OW)}
 
 
+# =====================================================================================================================
+# TMA geometry (conv_tma.cu): M tiles = whole images or strips of image rows, so one im2col tile of one tap is one TMA box
+# =====================================================================================================================
+SWIZZLE_128B, SWIZZLE_128B_ATOM_32B = 3, 4
+
+
+def tma_plan(mode: int, g: ConvGeom, arena_stride: int, S: int) -> Optional[Dict]:
+    """Extra launch fields + tensor-map specs of the TMA-fed kernel, or ``None`` when this layer needs the cp.async gather
+    (first layers with padded channels, channel counts that are not multiples of 32, dgrad of strided convolutions, wide maps).
+
+    ``maps`` entries are ``(operand, dims, strides_bytes, box, elem_strides, swizzle)`` with the activation group stride left
+    symbolic (``None``): the caller substitutes its buffers' group strides and base addresses."""
+    s = g.stride
+    if g.Cin != g.Cin_pad or g.Cin % 32 or g.wrow % 4:
+        return None
+
+    def tile(RH: int, RW: int):
+        hw = RH * RW
+        if hw <= 128:
+            Bt = 128 // hw
+            return dict(Bt=Bt, TH=RH, tpi=1, RT=Bt * hw, mtiles=(g.B + Bt - 1) // Bt)
+        if RW > 128:
+            return None
+        TH = 128 // RW
+        tpi = (RH + TH - 1) // TH
+        return dict(Bt=1, TH=TH, tpi=tpi, RT=TH * RW, mtiles=g.B * tpi)
+
+    act = lambda C, W, H: ([C, W, H, g.B, None], [C * 4, W * C * 4, H * W * C * 4, None])
+    if mode == MODE_F:
+        t = tile(g.OH, g.OW)
+        if t is None or g.OW * s > 256 or t["TH"] * s > 256:
+            return None
+        dims, strides = act(g.Cin_pad, g.IW, g.IH)
+        t.update(RH=g.OH, RW=g.OW, sgn=1, off=-g.pad, kb_total=len(g.live_taps()) * (g.Cin // 32),
+                 maps=[("X", dims, strides, [32, g.OW * s, t["TH"] * s, t["Bt"], 1], [1, s, s, 1, 1], SWIZZLE_128B),
+                       ("W", [g.wrow, g.Cout, S], [g.wrow * 4, arena_stride * 4], [32, _bn_tile(g.Cout), 1], [1, 1, 1], SWIZZLE_128B)])
+        return t
+    if mode == MODE_D:
+        if s != 1 or g.Cout != g.Cout_pad or g.Cout % 32:
+            return None
+        t = tile(g.IH, g.IW)
+        if t is None:
+            return None
+        dims, strides = act(g.Cout_pad, g.OW, g.OH)
+        T = g.KH * g.KW
+        t.update(RH=g.IH, RW=g.IW, sgn=-1, off=g.pad, kb_total=len(g.live_taps()) * (g.Cout // 32),
+                 maps=[("X", dims, strides, [32, g.IW, t["TH"], t["Bt"], 1], [1, 1, 1, 1, 1], SWIZZLE_128B),
+                       ("W", [g.Cin, T, g.Cout, S], [g.Cin * 4, g.wrow * 4, arena_stride * 4], [32, 1, 32, 1], [1, 1, 1, 1], SWIZZLE_128B_ATOM_32B)])
+        return t
+    # ---- W: reduction over boxes of <= 32 output pixels ----
+    if g.OW > 32 or g.OW * s > 256:
+        return None
+    hw = g.OH * g.OW
+    if hw <= 32:
+        bb, bh, bpi = 32 // hw, g.OH, 1
+        kb = (g.B + bb - 1) // bb
+    else:
+        bb, bh = 1, max(1, 32 // g.OW)
+        bpi = (g.OH + bh - 1) // bh
+        kb = g.B * bpi
+    if bh * s > 256:
+        return None
+    dx, sx = act(g.Cin_pad, g.IW, g.IH)
+    dy, sy = act(g.Cout_pad, g.OW, g.OH)
+    return dict(PK=bb * bh * g.OW, bh=bh, bb=bb, bpi=bpi, kb_total=kb,
+                maps=[("X", dx, sx, [32, g.OW * s, bh * s, bb, 1], [1, s, s, 1, 1], SWIZZLE_128B_ATOM_32B),
+                      ("Y", dy, sy, [32, g.OW, bh, bb, 1], [1, 1, 1, 1, 1], SWIZZLE_128B_ATOM_32B)])
+
+
 def grid_of(plan: Dict, G: int = 1) -> tuple:
     m_ext = plan["M"] + (1 if plan["mode"] == MODE_W and plan.get("ones_row") else 0)
     return ((m_ext + BM - 1) // BM, (plan["N"] + plan["BN"] - 1) // plan["BN"], G)

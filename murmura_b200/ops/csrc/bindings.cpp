@@ -74,6 +74,9 @@ void dmtt_update(Tensor adj, Tensor claims, Tensor collab, Tensor received, Tens
 
 // conv_tcgen05.cu / layers.cu (plans are dicts built by murmura_b200/ops/conv_plan.py and parallel/fused_trainer.py)
 int64_t conv_gemm(py::dict plan);
+int64_t conv_tma(py::dict plan);
+py::bytes tma_encode(int64_t ptr, std::vector<int64_t> dims, std::vector<int64_t> strides_bytes, std::vector<int64_t> box,
+                     std::vector<int64_t> elem_strides, int64_t swizzle);
 void gather_grouped(py::dict d);
 void bn_fwd_grouped(py::dict d);
 void bn_bwd_grouped(py::dict d);
@@ -124,6 +127,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("liar_claims", &liar_claims);
     m.def("dmtt_update", &dmtt_update);
     m.def("conv_gemm", &conv_gemm, "grouped implicit-GEMM conv / linear layer on tcgen05 (fprop, dgrad, wgrad + SGD)");
+    m.def("conv_tma", &conv_tma, "TMA-fed grouped implicit-GEMM conv / linear layer on tcgen05");
+    m.def("tma_encode", &tma_encode, "encode a tiled fp32 tensor map (rank <= 5)");
     m.def("gather_grouped", &gather_grouped);
     m.def("bn_fwd_grouped", &bn_fwd_grouped);
     m.def("bn_bwd_grouped", &bn_bwd_grouped);

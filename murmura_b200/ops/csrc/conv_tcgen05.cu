@@ -26,44 +26,11 @@
 #include <pybind11/pybind11.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "tc_common.cuh"
+#include "conv_common.cuh"
 
 namespace py = pybind11;
 
 namespace mb {
-using namespace mbtc;
-
-constexpr int kCgBM = 128;                      // UMMA M
-constexpr int kCgBK = 32;                       // fp32 per k-block = one 128-byte swizzle row
-constexpr int kCgStages = 4;
-constexpr int kCgLoaders = 128;                 // warps 0..3: operand gather, then epilogue
-constexpr int kCgThreads = 160;                 // warp 4: TMEM allocator + MMA issuer
-constexpr int kCgABytes = kCgBM * kCgBK * 4;    // 16 KiB
-
-enum { kModeF = 0, kModeD = 1, kModeW = 2 };
-
-struct ConvGemmParams {
-    const float* X; long long x_gs;             // gather source: input activations (F, W) / output gradient (D); group stride (elements)
-    float* Y; long long y_gs;                   // F, D: output [M][ldy];  W: the dY operand [P][ldy] (read only)
-    const float* R; long long r_gs;             // epilogue operand with the layout of Y: rmode 1 = residual added before the activation (F),
-    int rmode;                                  //   rmode 2 = ReLU mask, out *= (R > 0) (D: gradient through a ReLU fused into the producer)
-    float* arena; long long arena_gs;           // arena rows: base of group g = row_tab ? row_tab[g] : arena + (gmap ? gmap[g] : g)·arena_gs
-    const long long* row_tab; const int* gmap;
-    long long w_off, bias_off, bn_mean_off, bn_var_off, bn_gamma_off, bn_beta_off;   // element offsets in a row; < 0 = absent
-    const int* ptab;                            // packed (b << 16 | y << 8 | x) per GEMM row (F, D) / per reduction index (W)
-    const float* ones;                          // ≥ 4 floats of 1.0 (bias-gradient row of W mode)
-    int M, N, K;
-    int splitk, kb_total, kb_per_split;
-    int SH, SW, C, lds;                         // source plane; k-decode modulus (channels per tap); floats between source pixels
-    int KW, stride, pad, ntaps;
-    int Cw_real, wrow;                          // weight channels per tap, floats per output-channel row (KH·KW·Cin)
-    int Ck_real;                                // D: real output channels (k-decode modulus C may be the padded count)
-    int ldy;
-    float alpha, eps;
-    int relu, act, accumulate, vecB, ones_row;
-    int mn_swap;                                // debug: swap the LBO / SBO roles of MN-major descriptors (ops/selfcheck.py probes it)
-    unsigned char taps[64];
-};
 
 // Source pixel of GEMM row (b, y, x) for tap (kh, kw).  F / W: the input pixel under the tap; D: the output pixel whose
 // tap (kh, kw) lands on input pixel (y, x) (exists only when the offset is a multiple of the stride).
@@ -210,6 +177,9 @@ __device__ __forceinline__ void load_b_grad(const ConvGemmParams& p, const float
     }
 }
 
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define CG_STAMP(slot) do { if (p.dbg) p.dbg[(((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); } while (0)
+
 template <int MODE, int BN>
 __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     constexpr int NS = kCgStages, LOOK = kCgStages - 1;
@@ -223,6 +193,7 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) CG_STAMP(0);
     const int g = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - g * p.splitk;
     const int m0 = (int)blockIdx.x * kCgBM, n0 = (int)blockIdx.y * BN;
     const int kb_begin = split * p.kb_per_split;
@@ -241,6 +212,7 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (tid == 0) CG_STAMP(1);
 
     float* row = p.row_tab ? reinterpret_cast<float*>(p.row_tab[g]) : p.arena + (long long)(p.gmap ? p.gmap[g] : g) * p.arena_gs;
     float* Wg = row + p.w_off;
@@ -269,6 +241,7 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
                 }
             }
             cp_async_commit();
+            if (tid == 0 && it == 0) CG_STAMP(2);
             if (it >= LOOK) {
                 cp_async_wait<LOOK>();                          // this thread's copies of k-block it−LOOK have landed
                 fence_proxy_async();
@@ -276,75 +249,13 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
             }
         }
         // ================= epilogue: TMEM → registers → global =================
+        if (tid == 0) CG_STAMP(3);
         mbar_wait_backoff(&accum_bar, 0);
         tc_fence_after();
+        if (tid == 0) CG_STAMP(5);
         const int r = m0 + warp * 32 + lane;
-        if (MODE != kModeW) {
-            const bool rvalid = r < p.M;
-            float* yrow = Yg + (long long)r * p.ldy;
-            const float* rrow = p.R ? p.R + (long long)g * p.r_gs + (long long)r * p.ldy : nullptr;
-            const bool atomic = p.accumulate || p.splitk > 1;
-            const bool lead = split == 0;
-            const float* bias = (p.bias_off >= 0 && lead) ? row + p.bias_off : nullptr;
-            const bool bn = p.bn_mean_off >= 0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-                if (!rvalid || n0 + c0 >= p.N) continue;
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int col = n0 + c0 + i;
-                    float x = __uint_as_float(v[i]) * p.alpha;
-                    if (col < p.N) {
-                        if (bias) x += bias[col];
-                        if (bn) {
-                            const float g_ = p.bn_gamma_off >= 0 ? row[p.bn_gamma_off + col] : 1.f;
-                            const float b_ = p.bn_beta_off >= 0 ? row[p.bn_beta_off + col] : 0.f;
-                            x = (x - row[p.bn_mean_off + col]) * rsqrtf(row[p.bn_var_off + col] + p.eps) * g_ + b_;
-                        }
-                        if (rrow) { if (p.rmode == 2) x = rrow[col] > 0.f ? x : 0.f; else x += rrow[col]; }
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        else if (p.act == 2) x = (x > 20.f ? x : log1pf(__expf(x))) + 1.f;       // Dirichlet head: softplus + 1
-                    }
-                    f[i] = x;
-                }
-                const bool full = n0 + c0 + 16 <= p.N && (p.ldy & 3) == 0;
-                if (full) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        if (atomic) red_add_v4(yrow + n0 + c0 + i, f[i], f[i + 1], f[i + 2], f[i + 3]);
-                        else *reinterpret_cast<float4*>(yrow + n0 + c0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int col = n0 + c0 + i;
-                        if (col < p.N) { if (atomic) red_add_f32(yrow + col, f[i]); else yrow[col] = f[i]; }
-                    }
-                }
-            }
-        } else {
-            // rows = (tap, ci) → W[col][tap][ci] += α·acc  (32 lanes = 32 consecutive ci: coalesced reductions); bias row → b[col]
-            const int Mreal = p.ntaps * p.C;
-            float* target = nullptr; long long cstride = 0;
-            if (r < Mreal) {
-                const int lt = r / p.C, cc = r - lt * p.C;
-                if (cc < p.Cw_real) { target = Wg + (int)p.taps[lt] * p.Cw_real + cc; cstride = p.wrow; }
-            } else if (r == Mreal && p.ones_row && p.bias_off >= 0) { target = row + p.bias_off; cstride = 1; }
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-                if (target == nullptr) continue;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int col = n0 + c0 + i;
-                    if (col < p.N) red_add_f32(target + (long long)col * cstride, __uint_as_float(v[i]) * p.alpha);
-                }
-            }
-        }
+        if (MODE != kModeW) epilogue_rows<BN>(p, tmem_base, warp, r < p.M ? (long long)r : -1ll, n0, g, split, row, Yg);
+        else epilogue_wgrad<BN>(p, tmem_base, warp, r, n0, row);
     } else if (lane == 0) {
         // ================= MMA issuer: 4 × (128 × BN × 8) tf32 MMAs per k-block =================
         constexpr uint32_t idesc = umma_idesc_tf32(kCgBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
@@ -352,6 +263,7 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
             const int s = it % NS;
             mbar_wait(&full_bar[s], (uint32_t)((it / NS) & 1));
             tc_fence_after();
+            if (it == 0) CG_STAMP(4);
             const uint32_t sa = smem0 + s * STAGE, sb = sa + kCgABytes;
 #pragma unroll
             for (int k = 0; k < kCgBK / 8; ++k) {
@@ -369,16 +281,16 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
         }
         umma_commit(&accum_bar);
     }
+    if (tid == 0) CG_STAMP(6);
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc<BN>(tmem_base);
+    if (tid == 0) CG_STAMP(7);
 }
 
 }  // namespace mb
 
 namespace {
-
-template <typename T> T dget(const py::dict& d, const char* k, T def) { return d.contains(k) ? d[k].cast<T>() : def; }
 
 template <int MODE, int BN>
 void launch_conv(const mb::ConvGemmParams& p, dim3 grid, cudaStream_t stream) {
@@ -398,47 +310,11 @@ void launch_conv(const mb::ConvGemmParams& p, dim3 grid, cudaStream_t stream) {
 // Pointers travel as integers (sub-buffers of the trainer's workspace / the arena); returns the number of CTAs.
 int64_t conv_gemm(py::dict d) {
     mb::ConvGemmParams p;
-    memset(&p, 0, sizeof(p));
-    const int mode = d["mode"].cast<int>();
-    const int G = d["G"].cast<int>();
-    const int bn = dget<int>(d, "BN", 64);
-    p.X = reinterpret_cast<const float*>(d["X"].cast<int64_t>()); p.x_gs = d["x_gs"].cast<int64_t>();
-    p.Y = reinterpret_cast<float*>(d["Y"].cast<int64_t>()); p.y_gs = d["y_gs"].cast<int64_t>();
-    p.R = reinterpret_cast<const float*>(dget<int64_t>(d, "R", 0)); p.r_gs = dget<int64_t>(d, "r_gs", 0); p.rmode = dget<int>(d, "rmode", 1);
-    p.arena = reinterpret_cast<float*>(d["arena"].cast<int64_t>()); p.arena_gs = d["arena_gs"].cast<int64_t>();
-    p.row_tab = reinterpret_cast<const long long*>(dget<int64_t>(d, "row_tab", 0));
-    p.gmap = reinterpret_cast<const int*>(dget<int64_t>(d, "gmap", 0));
-    p.w_off = d["w_off"].cast<int64_t>(); p.bias_off = dget<int64_t>(d, "bias_off", -1);
-    p.bn_mean_off = dget<int64_t>(d, "bn_mean_off", -1); p.bn_var_off = dget<int64_t>(d, "bn_var_off", -1);
-    p.bn_gamma_off = dget<int64_t>(d, "bn_gamma_off", -1); p.bn_beta_off = dget<int64_t>(d, "bn_beta_off", -1);
-    p.ptab = reinterpret_cast<const int*>(d["ptab"].cast<int64_t>());
-    p.ones = reinterpret_cast<const float*>(dget<int64_t>(d, "ones", 0));
-    p.M = d["M"].cast<int>(); p.N = d["N"].cast<int>(); p.K = d["K"].cast<int>();
-    p.splitk = dget<int>(d, "splitk", 1);
-    p.SH = d["SH"].cast<int>(); p.SW = d["SW"].cast<int>(); p.C = d["C"].cast<int>(); p.lds = d["lds"].cast<int>();
-    p.KW = d["KW"].cast<int>(); p.stride = d["stride"].cast<int>(); p.pad = d["pad"].cast<int>();
-    p.Cw_real = d["Cw_real"].cast<int>(); p.wrow = d["wrow"].cast<int>(); p.Ck_real = dget<int>(d, "Ck_real", p.C);
-    p.ldy = d["ldy"].cast<int>();
-    p.alpha = dget<float>(d, "alpha", 1.f); p.eps = dget<float>(d, "eps", 1e-5f);
-    p.relu = dget<int>(d, "relu", 0); p.act = dget<int>(d, "act", 0); p.accumulate = dget<int>(d, "accumulate", 0);
-    p.vecB = dget<int>(d, "vecB", 4); p.ones_row = dget<int>(d, "ones_row", 0); p.mn_swap = dget<int>(d, "mn_swap", 0);
-    auto taps = d["taps"].cast<std::vector<int>>();
-    TORCH_CHECK(!taps.empty() && taps.size() <= 64, "conv_gemm: 1..64 live taps");
-    p.ntaps = (int)taps.size();
-    for (size_t i = 0; i < taps.size(); ++i) p.taps[i] = (unsigned char)taps[i];
-
-    TORCH_CHECK(mode >= 0 && mode <= 2 && (bn == 64 || bn == 128) && G >= 1 && p.M > 0 && p.N > 0 && p.K > 0, "conv_gemm: bad plan");
-    TORCH_CHECK(p.C % 4 == 0 && p.lds % 4 == 0 && p.ldy % 4 == 0, "conv_gemm: channel counts / leading dimensions must be multiples of 4");
+    int mode, G, bn;
+    mbhost::fill_conv_params(d, p, mode, G, bn);
     TORCH_CHECK(p.stride >= 1 && p.SH <= 256 && p.SW <= 256 && p.ptab != nullptr);
     TORCH_CHECK(p.vecB == 4 || (mode == mb::kModeF), "conv_gemm: 4-byte weight copies exist for fprop only");
     if (mode == mb::kModeW) TORCH_CHECK(!p.ones_row || p.ones != nullptr, "conv_gemm: ones buffer missing");
-    const bool fused_act = p.relu || p.act || p.bn_mean_off >= 0 || (p.R && p.rmode == 1);
-    TORCH_CHECK(!(fused_act || p.R) || p.splitk == 1, "conv_gemm: fused epilogues need the complete sum in one CTA (splitk = 1)");
-    TORCH_CHECK(!(fused_act && p.accumulate), "conv_gemm: activations cannot be applied to an accumulating output");
-    p.kb_total = (p.K + mb::kCgBK - 1) / mb::kCgBK;
-    p.splitk = std::max(1, std::min(p.splitk, p.kb_total));
-    p.kb_per_split = (p.kb_total + p.splitk - 1) / p.splitk;
-    p.splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;                 // no empty slice
     const int m_ext = mode == mb::kModeW ? p.M + (p.ones_row ? 1 : 0) : p.M;
     dim3 grid((unsigned)((m_ext + mb::kCgBM - 1) / mb::kCgBM), (unsigned)((p.N + bn - 1) / bn), (unsigned)(G * p.splitk));
     TORCH_CHECK(grid.z <= 65535 && grid.y <= 65535, "conv_gemm: grid too large");

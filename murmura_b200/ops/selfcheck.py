@@ -54,12 +54,15 @@ def _nhwc(x: torch.Tensor, cpad: int) -> torch.Tensor:
 
 
 class Harness:
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, tma: bool = False):
         from murmura_b200 import ops
         self.ext = ops.ext()
         self.dev = device
         self.ones = torch.ones(16, device=device)
         self.ptabs: Dict = {}
+        self.tma = tma
+        self._tma: Dict = {}
+        self.tma_used = 0
 
     def ptab(self, shape):
         if shape not in self.ptabs:
@@ -67,7 +70,26 @@ class Harness:
         return self.ptabs[shape]
 
     def launch(self, plan: Dict, G: int, X: torch.Tensor, Y: torch.Tensor, arena: torch.Tensor, gmap: Optional[torch.Tensor] = None,
-               R: Optional[torch.Tensor] = None, **kw) -> int:
+               R: Optional[torch.Tensor] = None, geom: Optional[cp.ConvGeom] = None, **kw) -> int:
+        if self.tma and geom is not None:
+            from murmura_b200.ops.conv_launch import encode_tma
+            key = (geom, plan["mode"], X.data_ptr(), Y.data_ptr(), arena.data_ptr())
+            if key not in self._tma:
+                self._tma[key] = encode_tma(self.ext, plan["mode"], geom, x_ptr=X.data_ptr(), x_gs=X.stride(0), y_ptr=Y.data_ptr(), y_gs=Y.stride(0),
+                                            w_ptr=arena.data_ptr() + plan["w_off"] * 4, arena_stride=arena.stride(0), slots=arena.shape[0],
+                                            groups=X.shape[0])
+            extra = self._tma[key]
+            if extra is not None:
+                d = {k: v for k, v in plan.items() if k != "ptab_shape"}
+                d.update(G=G, X=X.data_ptr(), x_gs=X.stride(0), Y=Y.data_ptr(), y_gs=Y.stride(0), arena=arena.data_ptr(), arena_gs=arena.stride(0),
+                         ones=self.ones.data_ptr())
+                if gmap is not None:
+                    d["gmap"] = gmap.data_ptr()
+                if R is not None:
+                    d.update(R=R.data_ptr(), r_gs=R.stride(0))
+                d.update(kw); d.update(extra)
+                self.tma_used += 1
+                return int(self.ext.conv_tma(d))
         d = {k: v for k, v in plan.items() if k != "ptab_shape"}
         d.update(G=G, X=X.data_ptr(), x_gs=X.stride(0) if X.dim() > 1 else 0, Y=Y.data_ptr(), y_gs=Y.stride(0) if Y.dim() > 1 else 0,
                  arena=arena.data_ptr(), arena_gs=arena.stride(0), ptab=self.ptab(plan["ptab_shape"]).data_ptr(), ones=self.ones.data_ptr())
@@ -117,7 +139,7 @@ def check_case(h: Harness, case: Tuple, mode: str, G: int = 1, splitk: int = 1, 
         if mode == "F":
             plan = cp.plan_fprop(g); plan.update(w_off=w_off, bias_off=b_off, relu=1 if splitk == 1 else 0, splitk=splitk)
             Y = torch.zeros(G, plan["M"] * plan["ldy"], device=dev)
-            ctas = h.launch(plan, G, X, Y, arena, gmap)
+            ctas = h.launch(plan, G, X, Y, arena, gmap, geom=g)
             ref = torch.stack([F.conv2d(x[i], w[order[i]], b[order[i]], stride=s, padding=p) for i in range(G)])
             if splitk == 1:
                 ref = F.relu(ref)
@@ -128,7 +150,7 @@ def check_case(h: Harness, case: Tuple, mode: str, G: int = 1, splitk: int = 1, 
                 return {"case": name, "mode": mode, "skipped": "first layer"}
             plan = cp.plan_dgrad(g); plan.update(w_off=w_off, splitk=splitk, accumulate=1, mn_swap=mn_swap)
             Y = torch.full((G, plan["M"] * plan["ldy"]), 0.25, device=dev)
-            ctas = h.launch(plan, G, DY, Y, arena, gmap)
+            ctas = h.launch(plan, G, DY, Y, arena, gmap, geom=g)
             xs = x.clone().requires_grad_(True)
             ref = torch.stack([torch.autograd.grad(F.conv2d(xs[i], w[order[i]], None, stride=s, padding=p), xs, dy[i])[0][i] for i in range(G)]) + 0.25
             got = Y.view(G, B, H, W, g.Cin_pad)[..., :Cin].permute(0, 1, 4, 2, 3)
@@ -136,7 +158,7 @@ def check_case(h: Harness, case: Tuple, mode: str, G: int = 1, splitk: int = 1, 
         else:
             plan = cp.plan_wgrad(g, bias=True); plan.update(w_off=w_off, bias_off=b_off, alpha=-1.0, splitk=splitk, mn_swap=mn_swap)
             before = arena.clone()
-            ctas = h.launch(plan, G, X, DY, arena, gmap)
+            ctas = h.launch(plan, G, X, DY, arena, gmap, geom=g)
             ws = w.clone().requires_grad_(True); bs = b.clone().requires_grad_(True)
             dws, dbs = [], []
             for i in range(G):
@@ -152,7 +174,7 @@ def check_case(h: Harness, case: Tuple, mode: str, G: int = 1, splitk: int = 1, 
             pad_ok = bool((delta[~touched] == 0).all()) and eb < 5e-3
         torch.cuda.synchronize()
         err = rel_err(got, ref)
-        out = {"case": name, "mode": mode, "G": G, "splitk": splitk, "ctas": ctas, "rel_err": err, "ok": bool(err < 5e-3 and pad_ok), "pad_ok": pad_ok,
+        out = {"case": name, "mode": mode, "G": G, "splitk": splitk, "ctas": ctas, "tma": h.tma_used, "rel_err": err, "ok": bool(err < 5e-3 and pad_ok), "pad_ok": pad_ok,
                "taps": len(plan["taps"]), "K": plan["K"], "vecB": plan["vecB"]}
         if not out["ok"]:
             diff = (got - ref).abs()
@@ -166,7 +188,8 @@ def check_case(h: Harness, case: Tuple, mode: str, G: int = 1, splitk: int = 1, 
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def bench_case(h: Harness, case: Tuple, mode: str, G: int, iters: int = 30) -> Dict:
+def prepare_bench(h: Harness, case: Tuple, mode: str, G: int, splitk: Optional[int] = None):
+    """(launch closure, plan, geometry) of a benchmark launch of ``case`` in ``mode`` for ``G`` grouped nodes."""
     dev = h.dev
     g, x, w, b, dy, arena, w_off, b_off = make_case(case, G, dev)
     name, B, H, W, Cin, Cout, k, s, p = case
@@ -176,17 +199,27 @@ def bench_case(h: Harness, case: Tuple, mode: str, G: int, iters: int = 30) -> D
         plan = cp.plan_fprop(g); plan.update(w_off=w_off); src, dst = X, torch.zeros(G, plan["M"] * plan["ldy"], device=dev)
     elif mode == "D":
         if Cin != g.Cin_pad:
-            return {}
+            return None, None, g
         plan = cp.plan_dgrad(g); plan.update(w_off=w_off); src, dst = DY, torch.zeros(G, plan["M"] * plan["ldy"], device=dev)
     else:
         plan = cp.plan_wgrad(g, bias=True); plan.update(w_off=w_off, bias_off=b_off, alpha=-1e-6); src, dst = X, DY
     gx, gy, _ = cp.grid_of(plan, 1)
-    split = cp.choose_splitk(gx * gy * G, cp.kb_total(plan), 148, 2 if mode == "W" else 4)
+    split = cp.choose_splitk(gx * gy * G, cp.kb_total(plan), 148, 2 if mode == "W" else 4) if splitk is None else splitk
     plan["splitk"] = split
     if split > 1 and mode != "W":
         plan["accumulate"] = 1
+    return (lambda: h.launch(plan, G, src, dst, arena, geom=g)), plan, g
+
+
+def bench_case(h: Harness, case: Tuple, mode: str, G: int, iters: int = 30, splitk: Optional[int] = None) -> Dict:
+    dev = h.dev
+    name, B, H, W, Cin, Cout, k, s, p = case
+    launch, plan, g = prepare_bench(h, case, mode, G, splitk)
+    if launch is None:
+        return {}
+    split = plan["splitk"]
     for _ in range(3):
-        ctas = h.launch(plan, G, src, dst, arena)
+        ctas = launch()
     torch.cuda.synchronize()
     # the Python launch path costs more than these kernels run: time a CUDA graph of `reps` back-to-back launches
     reps = 20
@@ -195,7 +228,7 @@ def bench_case(h: Harness, case: Tuple, mode: str, G: int, iters: int = 30) -> D
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
         for _ in range(reps):
-            h.launch(plan, G, src, dst, arena)
+            launch()
     graph.replay(); torch.cuda.synchronize()
     ts = []
     for _ in range(iters // 3):
@@ -205,7 +238,7 @@ def bench_case(h: Harness, case: Tuple, mode: str, G: int, iters: int = 30) -> D
     ts.sort()
     flops = 2.0 * G * B * g.OH * g.OW * Cout * len(plan["taps"]) * Cin
     us = ts[len(ts) // 2]
-    return {"case": name, "mode": mode, "G": G, "us": round(us, 2), "us_min": round(ts[0], 2), "ctas": ctas, "splitk": split,
+    return {"case": name, "mode": mode, "G": G, "tma": h.tma_used > 0, "us": round(us, 2), "us_min": round(ts[0], 2), "ctas": ctas, "splitk": split,
             "tflops": round(flops / us / 1e6, 1), "kb": cp.kb_total(plan)}
 
 
@@ -215,10 +248,11 @@ def main(argv=None) -> int:
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--json", default=None)
     ap.add_argument("--mn-swap", type=int, default=0)
+    ap.add_argument("--tma", action="store_true", help="use the TMA-fed kernel wherever the geometry allows it")
     ap.add_argument("--cases", default=None, help="comma separated case-name prefixes")
     args = ap.parse_args(argv)
     dev = torch.device("cuda", 0)
-    h = Harness(dev)
+    h = Harness(dev, tma=args.tma)
     results, bench = [], []
     cases = [c for c in CASES if args.cases is None or c[0].startswith(tuple(args.cases.split(",")))]
     for mode in args.modes.split(","):

@@ -1294,7 +1294,71 @@ class B200Network:
                 else:
                     self.ext.ce_eval(out, yb, None, stats)
 
+    # ---- fused evaluation: every node's forward in ONE program (conv epilogues carry eval-BN / residual / ReLU) -----------------
+    def _fused_eval_setup(self):
+        from murmura_b200.parallel.fused_trainer import FusedForward
+        if not self.opt.fused_train or not self.nodes or self.opt.compute_dtype == "bf16" or not self.opt.cuda_graphs:
+            return None
+        first = self.nodes[0]
+        if (first.X.dim() == 4 and not first.nhwc) or any(vn.n == 0 for vn in self.nodes):
+            return None
+        shape = (first.X.shape[3], first.X.shape[1], first.X.shape[2]) if first.X.dim() == 4 else tuple(first.X.shape[1:])
+        n_max = max(vn.n for vn in self.nodes)
+        EB = min(max(1, self.opt.eval_batch), (n_max + 31) // 32 * 32)
+        fe = FusedForward(first.model, self.layout, self.live, EB, shape, self.V, evidential=self.evidential)
+        if not fe.supported or (self.evidential and not fe.evidential_head):
+            return None
+        order = sorted(range(self.V), key=lambda i: (-self.nodes[i].n, i))
+        chunks = (n_max + EB - 1) // EB
+        dev = self.device
+        fe.gmap = torch.tensor(order, dtype=torch.int32, device=dev)
+        perm = torch.zeros(self.V, chunks * EB, dtype=torch.int64)
+        for vn in self.nodes:
+            perm[vn.slot] = torch.arange(chunks * EB).clamp_max(vn.n - 1)
+        st = {"fe": fe, "order": torch.tensor(order, dtype=torch.int64, device=dev), "perm": perm.to(dev), "chunks": [],
+              "x_tab": torch.tensor([vn.X.data_ptr() for vn in self.nodes], dtype=torch.int64, device=dev),
+              "y_tab": torch.tensor([vn.y.data_ptr() for vn in self.nodes], dtype=torch.int64, device=dev), "graph": None}
+        for c in range(chunks):
+            valid = [min(EB, max(0, self.nodes[i].n - c * EB)) for i in order]
+            G = sum(1 for v in valid if v > 0)
+            st["chunks"].append((G, fe.eval_descriptors(valid[:G])))
+        return st
+
+    def _fused_eval_body(self, st) -> None:
+        fe = st["fe"]
+        fe.stats.zero_()
+        for c, (G, desc) in enumerate(st["chunks"]):
+            fe.load(G, st["x_tab"], st["y_tab"], st["perm"], c)
+            fe.forward(G)
+            fe.metrics(G, desc)
+        self.eval_stats.index_copy_(0, st["order"], fe.stats[: self.V])
+
+    def _evaluate_fused(self) -> bool:
+        if "_fused_eval" not in self.__dict__:
+            self._fused_eval = self._fused_eval_setup()
+        st = self._fused_eval
+        if st is None:
+            return False
+        fe = st["fe"]
+        if st["graph"] is None:
+            side = self.capture_streams[0]
+            side.wait_stream(torch.cuda.current_stream())
+            before = fe.be.launches
+            with torch.cuda.stream(side):
+                self._fused_eval_body(st)
+            st["launches"] = fe.be.launches - before
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._fused_eval_body(st)
+            st["graph"] = g
+        st["graph"].replay()
+        self.kernel_launches += st["launches"]
+        return True
+
     def _evaluate(self) -> List[Dict[str, Any]]:
+        if self._evaluate_fused():
+            return self._collect_metrics()
         self._fork()
         for i in self.launch_order:
             vn = self.nodes[i]
@@ -1308,6 +1372,9 @@ class B200Network:
                     self._eval_node(vn)
                 self.kernel_launches += (vn.n + max(1, self.opt.eval_batch) - 1) // max(1, self.opt.eval_batch)
         self._join()
+        return self._collect_metrics()
+
+    def _collect_metrics(self) -> List[Dict[str, Any]]:
         S = self.placement.slots_per_rank
         local = torch.zeros(S, _STAT_COLS, device=self.device)
         local[: self.V] = self.eval_stats[: self.V]
@@ -1568,7 +1635,7 @@ class B200Network:
             vn.train_graph = None; vn.eval_graph = None; vn.split_bwd = None
         self._evaluators.clear()                      # CUDA graphs / views that point into the arena must go before it does
         self.__dict__.pop("_batched_cache", None)
-        self.__dict__.pop("_fused_cache", None); self.__dict__.pop("fused", None)
+        self.__dict__.pop("_fused_cache", None); self.__dict__.pop("fused", None); self.__dict__.pop("_fused_eval", None)
         if self.world > 1:
             _dist().barrier()
         self.arena.close()

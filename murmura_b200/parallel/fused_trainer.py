@@ -65,7 +65,9 @@ class CudaBackend:
         self.device = device
         self.ones = torch.ones(16, device=device)
         self._ptabs: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self._tma: Dict[Any, Optional[Dict]] = {}
         self.launches = 0
+        self.tma_launches = 0
 
     def ptab(self, shape: Tuple[int, int, int]) -> torch.Tensor:
         t = self._ptabs.get(shape)
@@ -73,16 +75,31 @@ class CudaBackend:
             t = self._ptabs[shape] = torch.from_numpy(cp.pixel_table(*shape)).to(self.device)
         return t
 
-    def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab: Optional[torch.Tensor] = None) -> None:
+    def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab: Optional[torch.Tensor] = None,
+             geom: Optional[cp.ConvGeom] = None) -> None:
         d = {k: v for k, v in plan.items() if k != "ptab_shape"}
         d.update(G=G, X=X.ptr(), x_gs=X.gs, Y=Y.ptr(), y_gs=Y.gs, arena=tr.live.data_ptr(), arena_gs=tr.stride,
-                 gmap=tr.gmap.data_ptr(), ptab=self.ptab(plan["ptab_shape"]).data_ptr(), ones=self.ones.data_ptr())
+                 gmap=tr.gmap.data_ptr(), ones=self.ones.data_ptr())
         if R is not None:
             d.update(R=R.ptr(), r_gs=R.gs)
+        self.launches += 1
+        if geom is not None and row_tab is None and getattr(tr, "use_tma", True):
+            key = (geom, plan["mode"], X.ptr(), Y.ptr(), plan["w_off"])
+            if key not in self._tma:
+                from murmura_b200.ops.conv_launch import encode_tma
+                self._tma[key] = encode_tma(self.ext, plan["mode"], geom, x_ptr=X.ptr(), x_gs=X.gs, y_ptr=Y.ptr(), y_gs=Y.gs,
+                                            w_ptr=tr.live.data_ptr() + plan["w_off"] * 4, arena_stride=tr.stride,
+                                            slots=int(tr.live.shape[0]), groups=int(X.t.shape[0]))
+            extra = self._tma[key]
+            if extra is not None:
+                d.update(extra)
+                self.ext.conv_tma(d)
+                self.tma_launches += 1
+                return
+        d.update(ptab=self.ptab(plan["ptab_shape"]).data_ptr())
         if row_tab is not None:
             d.update(row_tab=row_tab.data_ptr(), gmap=0)
         self.ext.conv_gemm(d)
-        self.launches += 1
 
     def call(self, fn: str, d: Dict) -> None:
         getattr(self.ext, fn)(d)
@@ -102,7 +119,7 @@ class EmuBackend:
     def _np(buf: Buf, g: int) -> np.ndarray:
         return buf.t[g].numpy()
 
-    def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab=None) -> None:
+    def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab=None, geom=None) -> None:
         for g in range(G):
             row = tr.live[int(tr.gmap[g])].numpy()
             cp.emulate(plan, self._np(X, g), self._np(Y, g), row, None if R is None else self._np(R, g))
@@ -257,7 +274,7 @@ class ConvOp:
             p.update(bn_mean_off=self.bn["running_mean"], bn_var_off=self.bn["running_var"], bn_gamma_off=self.bn["weight"],
                      bn_beta_off=self.bn["bias"], eps=self.bn["eps"])
         assert split == 1 or self.y.pooled
-        tr.be.conv(tr, p, G, self.x, self.y, R=self.res, row_tab=getattr(tr, "row_tab", None))
+        tr.be.conv(tr, p, G, self.x, self.y, R=self.res, row_tab=getattr(tr, "row_tab", None), geom=self.geom)
 
     def bwd(self, tr: "FusedTrainer", G: int, lr: float) -> None:
         dy = self.y.grad
@@ -269,11 +286,11 @@ class ConvOp:
             assert not (split > 1 and not self.dgrad_accumulate) or self.x.grad.pooled
             if mask:
                 p.update(rmode=2)
-            tr.be.conv(tr, p, G, dy, self.x.grad, R=self.x if mask else None)
+            tr.be.conv(tr, p, G, dy, self.x.grad, R=self.x if mask else None, geom=self.geom)
         p = dict(self.pw)
         gx, gy, _ = cp.grid_of(p, 1)
         p.update(w_off=self.w_off, bias_off=self.bias_off, alpha=-lr, splitk=cp.choose_splitk(gx * gy * G, cp.kb_total(p), tr.target_ctas, min_kb=2))
-        tr.wgrad_launch(lambda: tr.be.conv(tr, p, G, self.x, dy))
+        tr.wgrad_launch(lambda: tr.be.conv(tr, p, G, self.x, dy, geom=self.geom))
 
 
 class BNOp:
@@ -841,3 +858,76 @@ class FusedTrainer:
         """Kernel launches of one round (all steps), counted while the program was captured / run."""
         per_step = len(self.ops) * 2 + 1
         return per_step * self.max_steps
+
+
+# =====================================================================================================================
+# inference tape: evaluation of the nodes' own models, scoring of foreign weight rows (UBAR stage 2 / EvidentialTrust / DMTT)
+# =====================================================================================================================
+class FusedForward:
+    """Forward-only program over groups.
+
+    A group is (weight row, data source): ``gmap[g]`` is the arena slot whose shard feeds the group (and whose weights are used
+    unless ``row_tab`` holds per-group row addresses — foreign candidates read in place from the published planes, local HBM or a
+    peer GPU over NVLink).  Eval-mode BatchNorm, residual adds, ReLU and the Dirichlet head are conv epilogues, so a ResNet-18
+    forward of every group is 21 conv launches + 1 pooling launch; ``metrics`` reduces the outputs to the engine's
+    ``[loss / sq-err, correct, count, vacuity, entropy, strength]`` rows on the device (``grouped_eval_kernel``).
+
+    Reference sites replaced: ``murmura/core/node.py:111-196`` (evaluation), ``murmura/aggregation/ubar.py:152-202``,
+    ``murmura/aggregation/evidential_trust.py:236-281``, ``murmura/dmtt/node_process.py:309-363`` (foreign-model scoring).
+    """
+
+    def __init__(self, model: nn.Module, layout, live: torch.Tensor, rows: int, sample_shape: Sequence[int], Gmax: int, *,
+                 evidential: bool = False, backend: Optional[Any] = None):
+        self.device = live.device
+        self.be = backend or (CudaBackend(self.device) if live.is_cuda else EmuBackend())
+        self.live, self.ints, self.stride = live, None, int(live.shape[1])
+        self.eb, self.seed = int(rows), 0
+        self.target_ctas = 0                            # every conv has its complete sum in one CTA (fused epilogues): no split-K
+        self.offsets = {e.name: e.offset for e in layout.entries if e.kind != "int"}
+        self.int_offsets = {e.name: e.offset for e in layout.entries if e.kind == "int"}
+        self.bufs, self.ops, self.bn_ops, self.pool_ops = [], [], [], []
+        self.evidential_head = False
+        self.logits = self.xb = None
+        self.npix = self.Csrc = self.Cdst = 0
+        self.row_tab: Optional[torch.Tensor] = None
+        try:
+            self.supported = build_program(self, model, self.eb, sample_shape, training=False)
+        except (_Unsupported, AssertionError) as exc:
+            self.supported, self.unsupported_reason = False, str(exc)
+        if not self.supported:
+            return
+        self.dirichlet = bool(evidential and self.evidential_head)
+        self.Gmax = max(int(Gmax), 1)
+        dev = self.device
+        for b in self.bufs:
+            b.t = torch.zeros(self.Gmax, b.size, device=dev)
+            b.gs = b.size
+        if self.be.name == "cuda":
+            for op in self.pool_ops:
+                op.idx = torch.zeros(self.Gmax, op.B * op.OH * op.OW * op.C, dtype=torch.uint8, device=dev)
+        self.gmap = torch.arange(self.Gmax, dtype=torch.int32, device=dev)
+        self.yb = torch.zeros(self.Gmax, self.eb, dtype=torch.int64, device=dev)
+        self.stats = torch.zeros(self.Gmax, 8, device=dev)
+        self.workspace_bytes = sum(b.t.numel() * 4 for b in self.bufs)
+
+    def load(self, G: int, x_tab: torch.Tensor, y_tab: torch.Tensor, perm: torch.Tensor, t: int) -> None:
+        """``xb[g] = X_{gmap[g]}[perm[gmap[g], t·rows : (t+1)·rows]]`` (+ labels) for the first ``G`` groups."""
+        self.be.call("gather_grouped", dict(G=G, x_tab=x_tab.data_ptr(), y_tab=y_tab.data_ptr(), perm=perm.data_ptr(), perm_ld=perm.shape[1],
+                                            gmap=self.gmap.data_ptr(), xb=self.xb.ptr(), xb_gs=self.xb.gs, yb=self.yb.data_ptr(),
+                                            yb_gs=self.yb.shape[1], t=t, eb=self.eb, npix=self.npix, Csrc=self.Csrc, Cdst=self.Cdst))
+
+    def forward(self, G: int) -> None:
+        for op in self.ops:
+            op.fwd(self, G)
+
+    def eval_descriptors(self, valid_rows: Sequence[int]) -> torch.Tensor:
+        """Device table for :meth:`metrics`: (outputs, labels, #valid rows) of every group."""
+        host = [[self.logits.ptr() + g * self.logits.gs * 4, self.yb.data_ptr() + g * self.yb.shape[1] * 8, int(v)] for g, v in enumerate(valid_rows)]
+        return torch.tensor(host or [[0, 0, 0]], dtype=torch.int64, device=self.device)
+
+    def metrics(self, G: int, desc: torch.Tensor, stats: Optional[torch.Tensor] = None, dirichlet: Optional[bool] = None) -> None:
+        """Accumulate the per-group metric rows (zero ``stats`` first).  ``dirichlet=False`` forces softmax-CE on the raw outputs
+        (UBAR scores even evidential models that way, reference ``aggregation/ubar.py:54,219``)."""
+        st = self.stats if stats is None else stats
+        self.be.ext.grouped_eval(desc, G, self.eb, self.logits.C, self.logits.ld, self.dirichlet if dirichlet is None else bool(dirichlet), st)
+        self.be.launches += 1
