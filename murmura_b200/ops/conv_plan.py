@@ -24,6 +24,10 @@ def ceil4(x: int) -> int:
     return (x + 3) // 4 * 4
 
 
+def ceil32(x: int) -> int:
+    return (x + 31) // 32 * 32
+
+
 @dataclass(frozen=True)
 class ConvGeom:
     """One conv (or linear: 1×1 map, 1×1 kernel) layer at a fixed batch size.  Activations are NHWC with ``Cin_pad`` /
@@ -44,7 +48,7 @@ class ConvGeom:
         object.__setattr__(self, "Cin_pad", self.Cin_pad or ceil4(self.Cin))
         object.__setattr__(self, "Cout_pad", self.Cout_pad or ceil4(self.Cout))
         assert self.Cin_pad % 4 == 0 and self.Cout_pad % 4 == 0 and self.Cin_pad >= self.Cin and self.Cout_pad >= self.Cout
-        assert self.IH <= 256 and self.IW <= 256 and self.B < 32768, "pixel table packs (b, y, x) as 15/8/8 bits"
+        assert self.IH <= 256 and self.IW <= 256, "feature maps are at most 256 x 256"
 
     @property
     def OH(self) -> int:
@@ -71,6 +75,7 @@ def linear_geom(B: int, K: int, N: int) -> ConvGeom:
 
 def pixel_table(B: int, H: int, W: int) -> np.ndarray:
     """``b << 16 | y << 8 | x`` for every pixel of a [B, H, W] plane, row-major."""
+    assert B < 32768 and H <= 256 and W <= 256, "pixel table packs (b, y, x) as 15/8/8 bits"
     b, y, x = np.meshgrid(np.arange(B), np.arange(H), np.arange(W), indexing="ij")
     return ((b << 16) | (y << 8) | x).astype(np.int32).ravel()
 
@@ -124,7 +129,7 @@ def tma_plan(mode: int, g: ConvGeom, arena_stride: int, S: int) -> Optional[Dict
     ``maps`` entries are ``(operand, dims, strides_bytes, box, elem_strides, swizzle)`` with the activation group stride left
     symbolic (``None``): the caller substitutes its buffers' group strides and base addresses."""
     s = g.stride
-    if g.Cin != g.Cin_pad or g.Cin % 32 or g.wrow % 4:
+    if g.Cin_pad % 32 or (mode != MODE_W and (g.Cin != g.Cin_pad or g.wrow % 4)):
         return None
 
     def tile(RH: int, RW: int):
@@ -139,25 +144,38 @@ def tma_plan(mode: int, g: ConvGeom, arena_stride: int, S: int) -> Optional[Dict
         return dict(Bt=1, TH=TH, tpi=tpi, RT=TH * RW, mtiles=g.B * tpi)
 
     act = lambda C, W, H: ([C, W, H, g.B, None], [C * 4, W * C * 4, H * W * C * 4, None])
+    live = g.live_taps()
     if mode == MODE_F:
         t = tile(g.OH, g.OW)
-        if t is None or g.OW * s > 256 or t["TH"] * s > 256:
+        if t is None or g.OW * s > 256 or t["TH"] * s > 256 or len(live) > 32:
             return None
         dims, strides = act(g.Cin_pad, g.IW, g.IH)
-        t.update(RH=g.OH, RW=g.OW, sgn=1, off=-g.pad, kb_total=len(g.live_taps()) * (g.Cin // 32),
+        cls = dict(py=0, px=0, taps=live, dx=[tp % g.KW - g.pad for tp in live], dy=[tp // g.KW - g.pad for tp in live])
+        t.update(RH=g.OH, RW=g.OW, OPH=g.OH, OPW=g.OW, osc=1, ystep=s, classes=[cls], kb_total=len(live) * (g.Cin // 32),
                  maps=[("X", dims, strides, [32, g.OW * s, t["TH"] * s, t["Bt"], 1], [1, s, s, 1, 1], SWIZZLE_128B),
                        ("W", [g.wrow, g.Cout, S], [g.wrow * 4, arena_stride * 4], [32, _bn_tile(g.Cout), 1], [1, 1, 1], SWIZZLE_128B)])
         return t
     if mode == MODE_D:
-        if s != 1 or g.Cout != g.Cout_pad or g.Cout % 32:
+        if g.Cout != g.Cout_pad or g.Cout % 32 or g.IH % s or g.IW % s or s > 2:
             return None
-        t = tile(g.IH, g.IW)
+        # a stride-s dgrad = s² stride-1 problems over the parity classes of the input pixels
+        classes = []
+        for py in range(s):
+            for px in range(s):
+                taps = [tp for tp in live if (py + g.pad - tp // g.KW) % s == 0 and (px + g.pad - tp % g.KW) % s == 0]
+                if taps:
+                    classes.append(dict(py=py, px=px, taps=taps, dx=[(px + g.pad - tp % g.KW) // s for tp in taps],
+                                        dy=[(py + g.pad - tp // g.KW) // s for tp in taps]))
+        if not classes or max(len(c["taps"]) for c in classes) > 32:
+            return None
+        t = tile(g.IH // s, g.IW // s)
         if t is None:
             return None
         dims, strides = act(g.Cout_pad, g.OW, g.OH)
         T = g.KH * g.KW
-        t.update(RH=g.IH, RW=g.IW, sgn=-1, off=g.pad, kb_total=len(g.live_taps()) * (g.Cout // 32),
-                 maps=[("X", dims, strides, [32, g.IW, t["TH"], t["Bt"], 1], [1, 1, 1, 1, 1], SWIZZLE_128B),
+        t.update(RH=g.IH // s, RW=g.IW // s, OPH=g.IH, OPW=g.IW, osc=s, ystep=1, classes=classes,
+                 kb_total=max(len(c["taps"]) for c in classes) * (g.Cout // 32), partial=(len(classes) < s * s or s > 1),
+                 maps=[("X", dims, strides, [32, g.IW // s, t["TH"], t["Bt"], 1], [1, 1, 1, 1, 1], SWIZZLE_128B),
                        ("W", [g.Cin, T, g.Cout, S], [g.Cin * 4, g.wrow * 4, arena_stride * 4], [32, 1, 32, 1], [1, 1, 1, 1], SWIZZLE_128B_ATOM_32B)])
         return t
     # ---- W: reduction over boxes of <= 32 output pixels ----

@@ -78,6 +78,7 @@ int64_t conv_tma(py::dict plan);
 py::bytes tma_encode(int64_t ptr, std::vector<int64_t> dims, std::vector<int64_t> strides_bytes, std::vector<int64_t> box,
                      std::vector<int64_t> elem_strides, int64_t swizzle);
 void gather_grouped(py::dict d);
+void im2col_pack(py::dict d);
 void bn_fwd_grouped(py::dict d);
 void bn_bwd_grouped(py::dict d);
 void maxpool_fwd_grouped(py::dict d);
@@ -130,6 +131,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("conv_tma", &conv_tma, "TMA-fed grouped implicit-GEMM conv / linear layer on tcgen05");
     m.def("tma_encode", &tma_encode, "encode a tiled fp32 tensor map (rank <= 5)");
     m.def("gather_grouped", &gather_grouped);
+    m.def("im2col_pack", &im2col_pack, "mini-batch gather + im2col of the first layer + per-step packing of its weights");
     m.def("bn_fwd_grouped", &bn_fwd_grouped);
     m.def("bn_bwd_grouped", &bn_bwd_grouped);
     m.def("maxpool_fwd_grouped", &maxpool_fwd_grouped);

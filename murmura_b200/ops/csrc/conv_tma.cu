@@ -24,15 +24,23 @@ namespace mb {
 
 constexpr int kCtThreads = 192;
 
+// One tap set of modes F / D.  A stride-s dgrad is s² independent stride-1 problems, one per parity class (py, px) of the input
+// pixel: only the taps with kh ≡ py + pad (mod s) reach that class, and they read dY at a constant offset (dx, dy).
+struct TapClass { int ntaps, py, px; unsigned char tap[32]; signed char dx[32], dy[32]; };
+
 struct alignas(64) ConvTmaParams {
     CUtensorMap mapA;               // F: X {C,W,H,B,G};  D: dY {C,W,H,B,G};  W: X {C,W,H,B,G} (pixel-block box)
     CUtensorMap mapB;               // F: weights {K,Cout,S};  D: weights {Cin,T,Cout,S};  W: dY {C,W,H,B,G}
     ConvGemmParams g;
-    int RH, RW;                     // F / D: plane of the GEMM rows (F: output, D: input)
+    int RH, RW;                     // F / D: plane of the GEMM rows of one class (F: output plane, D: input plane / stride)
     int Bt, TH, tpi, RT;            // tile = Bt whole images (tpi == 1) or a strip of TH rows (tpi strips per image); RT rows
-    int sgn, off;                   // tap (kh, kw) → source start (sgn·kw + off, y0·stride + sgn·kh + off)
+    int ncls, mt_per_cls;           // classes share the grid: blockIdx.x = class · mt_per_cls + tile
+    int osc, OPH, OPW;              // output pixel of class row (y, x) = (y·osc + py, x·osc + px) in the [OPH, OPW] plane
+    int ystep;                      // source row of tile row y0 = y0·ystep + dy (F: conv stride, D: 1)
+    int nB;                         // images per node
     int PK, bh, bb, bpi;            // W: pixels per k-block = RW·bh·bb; k-blocks per image when bb == 1
     int prefill;                    // W: zero the stages before the first load (PK < 32) / write the all-ones bias atom
+    TapClass cls[4];
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -65,7 +73,10 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
     const int g = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - g * p.splitk;
     const int n0 = (int)blockIdx.y * BN;
     const int kb_begin = split * p.kb_per_split;
-    const int nkb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;
+    const int ci = MODE == kModeW ? 0 : (int)blockIdx.x / P.mt_per_cls;             // tap class of this CTA (F / D)
+    const TapClass& cls = P.cls[ci];
+    const int kb_total = MODE == kModeW ? p.kb_total : cls.ntaps * (p.C / kCgBK);
+    const int nkb = max(0, min(kb_total, kb_begin + p.kb_per_split) - kb_begin);    // 0: nothing to add for this slice
     const int slot = p.gmap ? p.gmap[g] : g;
     const uint32_t smem0 = smem_u32(smem);
 
@@ -103,8 +114,8 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
 
     // tile origin in the row space of modes F / D
     int b0 = 0, y0 = 0;
+    const int mt = MODE == kModeW ? 0 : (int)blockIdx.x - ci * P.mt_per_cls;
     if (MODE != kModeW) {
-        const int mt = (int)blockIdx.x;
         if (P.tpi == 1) b0 = mt * P.Bt;
         else { b0 = mt / P.tpi; y0 = (mt - b0 * P.tpi) * P.TH; }
     }
@@ -121,9 +132,8 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
                 if (MODE != kModeW) {
                     const int k = kb * kCgBK;
                     const int lt = k / p.C, c0 = k - lt * p.C;
-                    const int tap = p.taps[lt], kh = tap / p.KW, kw = tap - kh * p.KW;
-                    const int xs = P.sgn * kw + P.off;
-                    const int ys = (MODE == kModeF ? y0 * p.stride : y0) + P.sgn * kh + P.off;
+                    const int tap = cls.tap[lt];
+                    const int xs = cls.dx[lt], ys = y0 * P.ystep + cls.dy[lt];
                     mbar_expect_tx(&full_bar[s], (uint32_t)(P.RT * 128 + BN * 128));
                     tma_load_5d(sa, &P.mapA, c0, xs, ys, b0, g, &full_bar[s]);
                     if (MODE == kModeF) tma_load_3d_u(sb, &P.mapB, tap * p.Cw_real + c0, n0, slot, &full_bar[s]);
@@ -171,23 +181,29 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
                 }
                 umma_commit(&empty_bar[s]);
             }
-            umma_commit(&accum_bar);
+            if (nkb > 0) umma_commit(&accum_bar);
         }
     } else {
         // ================= epilogue =================
         float* row = p.arena + (long long)slot * p.arena_gs;
-        mbar_wait_backoff(&accum_bar, 0);
-        tc_fence_after();
-        const int r = warp * 32 + lane;
-        if (MODE != kModeW) {
-            long long grow = -1;
-            if (r < P.RT) {
-                if (P.tpi == 1) { grow = (long long)blockIdx.x * P.RT + r; if (grow >= p.M) grow = -1; }
-                else { const int y = y0 + r / P.RW; if (y < P.RH) grow = ((long long)b0 * P.RH + y) * P.RW + (r - (r / P.RW) * P.RW); }
+        if (nkb > 0) {
+            mbar_wait_backoff(&accum_bar, 0);
+            tc_fence_after();
+            const int r = warp * 32 + lane;
+            if (MODE != kModeW) {
+                long long grow = -1;
+                if (r < P.RT) {
+                    const int hw = P.RH * P.RW;
+                    const int bi = r / hw, rem = r - bi * hw;                 // whole-image tiles: bi-th image of the tile; strips: bi = 0
+                    const int y = y0 + rem / P.RW, x = rem - (rem / P.RW) * P.RW;
+                    const int b = b0 + bi;
+                    if (y < P.RH && b < P.nB)
+                        grow = ((long long)b * P.OPH + (y * P.osc + cls.py)) * P.OPW + (x * P.osc + cls.px);
+                }
+                epilogue_rows<BN>(p, tmem_base, warp, grow, n0, g, split, row, p.Y + (long long)g * p.y_gs);
+            } else {
+                epilogue_wgrad<BN>(p, tmem_base, warp, (int)blockIdx.x * kCgBM + r, n0, row);
             }
-            epilogue_rows<BN>(p, tmem_base, warp, grow, n0, g, split, row, p.Y + (long long)g * p.y_gs);
-        } else {
-            epilogue_wgrad<BN>(p, tmem_base, warp, (int)blockIdx.x * kCgBM + r, n0, row);
         }
     }
     tc_fence_before();
@@ -259,7 +275,23 @@ int64_t conv_tma(py::dict d) {
     using mbhost::dget;
     P.RH = dget<int>(d, "RH", 1); P.RW = dget<int>(d, "RW", 1);
     P.Bt = dget<int>(d, "Bt", 1); P.TH = dget<int>(d, "TH", 1); P.tpi = dget<int>(d, "tpi", 1); P.RT = dget<int>(d, "RT", 128);
-    P.sgn = dget<int>(d, "sgn", 1); P.off = dget<int>(d, "off", 0);
+    P.osc = dget<int>(d, "osc", 1); P.OPH = dget<int>(d, "OPH", P.RH); P.OPW = dget<int>(d, "OPW", P.RW); P.ystep = dget<int>(d, "ystep", 1);
+    P.ncls = 1; P.mt_per_cls = dget<int>(d, "mtiles", 1);
+    P.nB = P.g.M / std::max(1, P.OPH * P.OPW);
+    if (mode != mb::kModeW) {
+        auto classes = d["classes"].cast<std::vector<py::dict>>();
+        TORCH_CHECK(!classes.empty() && classes.size() <= 4, "conv_tma: 1..4 tap classes");
+        P.ncls = (int)classes.size();
+        for (int c = 0; c < P.ncls; ++c) {
+            auto taps = classes[c]["taps"].cast<std::vector<int>>();
+            auto dx = classes[c]["dx"].cast<std::vector<int>>();
+            auto dy = classes[c]["dy"].cast<std::vector<int>>();
+            TORCH_CHECK(!taps.empty() && taps.size() <= 32 && dx.size() == taps.size() && dy.size() == taps.size(), "conv_tma: 1..32 taps per class");
+            P.cls[c].ntaps = (int)taps.size(); P.cls[c].py = classes[c]["py"].cast<int>(); P.cls[c].px = classes[c]["px"].cast<int>();
+            for (size_t i = 0; i < taps.size(); ++i) { P.cls[c].tap[i] = (unsigned char)taps[i]; P.cls[c].dx[i] = (signed char)dx[i]; P.cls[c].dy[i] = (signed char)dy[i]; }
+        }
+        TORCH_CHECK(P.ncls == 1 || P.g.splitk == 1, "conv_tma: class launches do not split K");
+    }
     P.PK = dget<int>(d, "PK", 32); P.bh = dget<int>(d, "bh", 1); P.bb = dget<int>(d, "bb", 1); P.bpi = dget<int>(d, "bpi", 1);
     const mb::ConvGemmParams& p = P.g;
     TORCH_CHECK(p.row_tab == nullptr, "conv_tma: per-group row tables are not supported (use conv_gemm)");
@@ -270,7 +302,7 @@ int64_t conv_tma(py::dict d) {
         P.prefill = (P.PK < 32 || p.ones_row) ? 1 : 0;
         grid = dim3((unsigned)((Mreal + (p.ones_row ? 1 : 0) + mb::kCgBM - 1) / mb::kCgBM), (unsigned)((p.N + bn - 1) / bn), (unsigned)(G * p.splitk));
     } else {
-        grid = dim3((unsigned)d["mtiles"].cast<int>(), (unsigned)((p.N + bn - 1) / bn), (unsigned)(G * p.splitk));
+        grid = dim3((unsigned)(P.ncls * P.mt_per_cls), (unsigned)((p.N + bn - 1) / bn), (unsigned)(G * p.splitk));
     }
     TORCH_CHECK(grid.z <= 65535 && grid.y <= 65535, "conv_tma: grid too large");
     auto stream = at::cuda::getCurrentCUDAStream().stream();

@@ -73,6 +73,83 @@ __global__ void __launch_bounds__(256) gather_grouped_kernel(GatherArgs a) {
 }
 
 // =====================================================================================================================
+// first layer: mini-batch gather fused with im2col (+ per-step packing of the first layer's weights)
+//   xcol[g][(r, oh, ow)][k] = X_g[perm[..r]][ih][iw][c],  k = (kh·KW + kw)·Cin + c, zero outside the image and for k >= Kreal
+//   wpack[g][co][k] = W_slot[co][k] (k < Kreal, else 0), followed by the bias: rows of Kpad floats (a multiple of 32), so the
+//   first convolution / linear layer is a plain TMA-fed GEMM although its real K (7·7·3, 5·5·1, 561 …) is unaligned.
+// =====================================================================================================================
+struct Im2colArgs {
+    const long long* x_tab; const long long* y_tab; const long long* perm; long long perm_ld; const int* gmap;
+    float* xcol; long long xcol_gs; long long* yb; long long yb_gs;
+    long long* rng_step; unsigned int* ticket;
+    int t, eb, IH, IW, Cin, KH, KW, stride, pad, OH, OW, Kreal, Kpad;
+    const float* arena; long long arena_gs; const long long* row_tab; const int* wmap; long long w_off, bias_off;
+    long long bn_off[4];                                   // eval-mode BatchNorm of the first layer: mean, var, γ, β (or < 0)
+    float* wpack; long long wpack_gs; int Cout;
+};
+
+__global__ void __launch_bounds__(256) im2col_pack_kernel(Im2colArgs a) {
+    const int g = blockIdx.z, r = blockIdx.y;
+    const int K4 = a.Kpad >> 2;
+    if (r < a.eb) {
+        const int slot = a.gmap ? a.gmap[g] : g;
+        const long long src = a.perm[(long long)slot * a.perm_ld + (long long)a.t * a.eb + r];
+        const float* in = reinterpret_cast<const float*>(a.x_tab[slot]) + src * (long long)a.IH * a.IW * a.Cin;
+        const int P = a.OH * a.OW;
+        float* out = a.xcol + (long long)g * a.xcol_gs + (long long)r * P * a.Kpad;
+        const int total = P * K4;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+            const int pix = q / K4, k4 = (q - pix * K4) << 2;
+            const int oh = pix / a.OW, ow = pix - oh * a.OW;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k4 + j;
+                float x = 0.f;
+                if (k < a.Kreal) {
+                    const int tap = k / a.Cin, c = k - tap * a.Cin;
+                    const int kh = tap / a.KW, kw = tap - kh * a.KW;
+                    const int ih = oh * a.stride + kh - a.pad, iw = ow * a.stride + kw - a.pad;
+                    if (ih >= 0 && ih < a.IH && iw >= 0 && iw < a.IW) x = in[((long long)ih * a.IW + iw) * a.Cin + c];
+                }
+                v[j] = x;
+            }
+            *reinterpret_cast<float4*>(out + (long long)pix * a.Kpad + k4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            a.yb[(long long)g * a.yb_gs + r] = reinterpret_cast<const long long*>(a.y_tab[slot])[src];
+    } else if (a.wpack != nullptr) {
+        // weight packing block of this group
+        const float* row = a.row_tab ? reinterpret_cast<const float*>(a.row_tab[g]) : a.arena + (long long)(a.wmap ? a.wmap[g] : g) * a.arena_gs;
+        float* wp = a.wpack + (long long)g * a.wpack_gs;
+        const int total = a.Cout * K4;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+            const int co = q / K4, k4 = (q - co * K4) << 2;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (k4 + j < a.Kreal) ? row[a.w_off + (long long)co * a.Kreal + k4 + j] : 0.f;
+            *reinterpret_cast<float4*>(wp + (long long)co * a.Kpad + k4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        // per-channel vectors after the weights: bias, then BatchNorm mean / var / γ / β, ceil4(Cout) floats each
+        const int Cp = (a.Cout + 3) & ~3;
+        float* vec = wp + (long long)a.Cout * a.Kpad;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.Cout; i += gridDim.x * blockDim.x) {
+            if (a.bias_off >= 0) vec[i] = row[a.bias_off + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (a.bn_off[j] >= 0) vec[(j + 1) * Cp + i] = row[a.bn_off[j] + i];
+        }
+    }
+    if (a.rng_step != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int total_ctas = gridDim.x * gridDim.y * gridDim.z;
+            if (atomicAdd(a.ticket, 1u) == total_ctas - 1) { *a.ticket = 0u; *a.rng_step += 1; }
+        }
+    }
+}
+
+// =====================================================================================================================
 // training BatchNorm (+residual) (+ReLU) (+dropout), grouped; the row splits of a channel tile form a thread-block cluster
 // and merge their partial sums through distributed shared memory (same scheme as bn_train.cu).
 // =====================================================================================================================
@@ -319,29 +396,42 @@ __device__ __forceinline__ long long pool_out_index(const PoolArgs& a, int b, in
     return a.nchw_out ? (((long long)b * a.C + c) * a.OH + oh) * a.OW + ow : (((long long)b * a.OH + oh) * a.OW + ow) * a.C + c;
 }
 
+// one thread = 4 consecutive channels of one output pixel (float4 loads / stores; no per-element div/mod chains)
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolArgs a) {
     const int g = blockIdx.y;
-    const long long total = (long long)a.B * a.OH * a.OW * a.C;
+    const int C4 = a.C >> 2;
+    const long long total = (long long)a.B * a.OH * a.OW * C4;
     const float* x = a.x + (long long)g * a.x_gs;
     float* y = a.y + (long long)g * a.y_gs;
     unsigned char* idx = a.idx + (long long)g * a.idx_gs;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % a.C); long long t = i / a.C;
+        const int c = (int)(i % C4) << 2; long long t = i / C4;
         const int ow = (int)(t % a.OW); t /= a.OW;
         const int oh = (int)(t % a.OH); const int b = (int)(t / a.OH);
-        float best = -INFINITY; int arg = 255;
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        int4 arg = make_int4(255, 255, 255, 255);
         for (int kh = 0; kh < a.k; ++kh) {
             const int ih = oh * a.stride + kh - a.pad;
             if (ih < 0 || ih >= a.H) continue;
             for (int kw = 0; kw < a.k; ++kw) {
                 const int iw = ow * a.stride + kw - a.pad;
                 if (iw < 0 || iw >= a.W) continue;
-                const float v = x[(((long long)b * a.H + ih) * a.W + iw) * a.C + c];
-                if (v > best || arg == 255) { best = v; arg = kh * a.k + kw; }      // first maximum in scan order (ATen's rule)
+                const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * a.H + ih) * a.W + iw) * a.C + c);
+                const int tap = kh * a.k + kw;                                   // first maximum in scan order (ATen's rule)
+                if (v.x > best.x || arg.x == 255) { best.x = v.x; arg.x = tap; }
+                if (v.y > best.y || arg.y == 255) { best.y = v.y; arg.y = tap; }
+                if (v.z > best.z || arg.z == 255) { best.z = v.z; arg.z = tap; }
+                if (v.w > best.w || arg.w == 255) { best.w = v.w; arg.w = tap; }
             }
         }
-        y[pool_out_index(a, b, oh, ow, c)] = best;
-        idx[i] = (unsigned char)arg;                                              // NHWC order regardless of the output layout
+        const long long o = (((long long)b * a.OH + oh) * a.OW + ow) * a.C + c;     // NHWC position (also the index-map position)
+        if (a.nchw_out) {
+            const long long hw = (long long)a.OH * a.OW, base = ((long long)b * a.C + c) * hw + (long long)oh * a.OW + ow;
+            y[base] = best.x; y[base + hw] = best.y; y[base + 2 * hw] = best.z; y[base + 3 * hw] = best.w;
+        } else {
+            *reinterpret_cast<float4*>(y + o) = best;
+        }
+        *reinterpret_cast<uchar4*>(idx + o) = make_uchar4((unsigned char)arg.x, (unsigned char)arg.y, (unsigned char)arg.z, (unsigned char)arg.w);
     }
 }
 
@@ -354,36 +444,48 @@ struct PoolBwdArgs {
 
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolBwdArgs a) {
     const int g = blockIdx.y;
-    const long long total = (long long)a.B * a.H * a.W * a.C;
+    const int C4 = a.C >> 2;
+    const long long total = (long long)a.B * a.H * a.W * C4;
     const float* dy = a.dy + (long long)g * a.dy_gs;
     const unsigned char* idx = a.idx + (long long)g * a.idx_gs;
     const float* x = a.x + (long long)g * a.x_gs;
     float* dx = a.dx + (long long)g * a.dx_gs;
+    const long long hw = (long long)a.OH * a.OW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % a.C); long long t = i / a.C;
+        const int c = (int)(i % C4) << 2; long long t = i / C4;
         const int iw = (int)(t % a.W); t /= a.W;
         const int ih = (int)(t % a.H); const int b = (int)(t / a.H);
-        float acc = 0.f;
-        if (!a.relu_mask || x[i] > 0.f) {
-            for (int kh = 0; kh < a.k; ++kh) {
-                const int th = ih + a.pad - kh;
-                if (th < 0 || th % a.stride != 0) continue;
-                const int oh = th / a.stride;
-                if (oh >= a.OH) continue;
-                for (int kw = 0; kw < a.k; ++kw) {
-                    const int tw = iw + a.pad - kw;
-                    if (tw < 0 || tw % a.stride != 0) continue;
-                    const int ow = tw / a.stride;
-                    if (ow >= a.OW) continue;
-                    if (idx[(((long long)b * a.OH + oh) * a.OW + ow) * a.C + c] == kh * a.k + kw) {
-                        const long long o = a.nchw_out ? (((long long)b * a.C + c) * a.OH + oh) * a.OW + ow
-                                                        : (((long long)b * a.OH + oh) * a.OW + ow) * a.C + c;
-                        acc += dy[o];
-                    }
-                }
+        const long long xi = (((long long)b * a.H + ih) * a.W + iw) * a.C + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = 0; kh < a.k; ++kh) {
+            const int th = ih + a.pad - kh;
+            if (th < 0 || th % a.stride != 0) continue;
+            const int oh = th / a.stride;
+            if (oh >= a.OH) continue;
+            for (int kw = 0; kw < a.k; ++kw) {
+                const int tw = iw + a.pad - kw;
+                if (tw < 0 || tw % a.stride != 0) continue;
+                const int ow = tw / a.stride;
+                if (ow >= a.OW) continue;
+                const long long o = (((long long)b * a.OH + oh) * a.OW + ow) * a.C + c;
+                const uchar4 id = *reinterpret_cast<const uchar4*>(idx + o);
+                const int tap = kh * a.k + kw;
+                float4 d;
+                if (a.nchw_out) {
+                    const long long base = ((long long)b * a.C + c) * hw + (long long)oh * a.OW + ow;
+                    d = make_float4(dy[base], dy[base + hw], dy[base + 2 * hw], dy[base + 3 * hw]);
+                } else d = *reinterpret_cast<const float4*>(dy + o);
+                if (id.x == tap) acc.x += d.x;
+                if (id.y == tap) acc.y += d.y;
+                if (id.z == tap) acc.z += d.z;
+                if (id.w == tap) acc.w += d.w;
             }
         }
-        dx[i] = acc;
+        if (a.relu_mask) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + xi);
+            acc.x = xv.x > 0.f ? acc.x : 0.f; acc.y = xv.y > 0.f ? acc.y : 0.f; acc.z = xv.z > 0.f ? acc.z : 0.f; acc.w = xv.w > 0.f ? acc.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(dx + xi) = acc;
     }
 }
 
@@ -575,6 +677,30 @@ void gather_grouped(py::dict d) {
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+void im2col_pack(py::dict d) {
+    mb::Im2colArgs a;
+    a.x_tab = lptr<const long long>(d, "x_tab"); a.y_tab = lptr<const long long>(d, "y_tab");
+    a.perm = lptr<const long long>(d, "perm"); a.perm_ld = d["perm_ld"].cast<int64_t>(); a.gmap = lptr<const int>(d, "gmap");
+    a.xcol = lptr<float>(d, "xcol"); a.xcol_gs = d["xcol_gs"].cast<int64_t>();
+    a.yb = lptr<long long>(d, "yb"); a.yb_gs = d["yb_gs"].cast<int64_t>();
+    a.rng_step = lptr<long long>(d, "rng_step"); a.ticket = lptr<unsigned int>(d, "ticket");
+    a.t = d["t"].cast<int>(); a.eb = d["eb"].cast<int>();
+    a.IH = d["IH"].cast<int>(); a.IW = d["IW"].cast<int>(); a.Cin = d["Cin"].cast<int>(); a.KH = d["KH"].cast<int>(); a.KW = d["KW"].cast<int>();
+    a.stride = d["stride"].cast<int>(); a.pad = d["pad"].cast<int>(); a.OH = d["OH"].cast<int>(); a.OW = d["OW"].cast<int>();
+    a.Kreal = d["Kreal"].cast<int>(); a.Kpad = d["Kpad"].cast<int>();
+    a.arena = lptr<const float>(d, "arena"); a.arena_gs = lget<int64_t>(d, "arena_gs", 0); a.row_tab = lptr<const long long>(d, "row_tab");
+    a.wmap = lptr<const int>(d, "wmap"); a.w_off = lget<int64_t>(d, "w_off", 0); a.bias_off = lget<int64_t>(d, "bias_off", -1);
+    a.bn_off[0] = lget<int64_t>(d, "bn_mean_off", -1); a.bn_off[1] = lget<int64_t>(d, "bn_var_off", -1);
+    a.bn_off[2] = lget<int64_t>(d, "bn_gamma_off", -1); a.bn_off[3] = lget<int64_t>(d, "bn_beta_off", -1);
+    a.wpack = lptr<float>(d, "wpack"); a.wpack_gs = lget<int64_t>(d, "wpack_gs", 0); a.Cout = lget<int>(d, "Cout", 0);
+    const int G = d["G"].cast<int>();
+    TORCH_CHECK(G >= 1 && a.eb >= 1 && a.Kpad % 4 == 0 && a.Kpad >= a.Kreal && (a.rng_step == nullptr || a.ticket != nullptr));
+    const long long work = (long long)a.OH * a.OW * (a.Kpad / 4);
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(32, (work + 255) / 256)), (unsigned)(a.eb + (a.wpack ? 1 : 0)), (unsigned)G);
+    mb::im2col_pack_kernel<<<grid, 256, 0, lstream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
 void bn_fwd_grouped(py::dict d) {
     mb::GbnFwdArgs a;
     a.x = lptr<const float>(d, "x"); a.res = lptr<const float>(d, "res"); a.y = lptr<float>(d, "y");
@@ -621,8 +747,8 @@ void maxpool_fwd_grouped(py::dict d) {
     a.OH = d["OH"].cast<int>(); a.OW = d["OW"].cast<int>(); a.k = d["k"].cast<int>(); a.stride = d["stride"].cast<int>(); a.pad = d["pad"].cast<int>();
     a.nchw_out = lget<int>(d, "nchw_out", 0);
     const int G = d["G"].cast<int>();
-    TORCH_CHECK(a.k * a.k < 255);
-    dim3 grid(gs_blocks((long long)a.B * a.OH * a.OW * a.C, G), G);
+    TORCH_CHECK(a.k * a.k < 255 && a.C % 4 == 0, "maxpool: C must be a multiple of 4");
+    dim3 grid(gs_blocks((long long)a.B * a.OH * a.OW * (a.C / 4), G), G);
     mb::maxpool_fwd_kernel<<<grid, 256, 0, lstream()>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
@@ -635,7 +761,8 @@ void maxpool_bwd_grouped(py::dict d) {
     a.OH = d["OH"].cast<int>(); a.OW = d["OW"].cast<int>(); a.k = d["k"].cast<int>(); a.stride = d["stride"].cast<int>(); a.pad = d["pad"].cast<int>();
     a.nchw_out = lget<int>(d, "nchw_out", 0); a.relu_mask = lget<int>(d, "relu_mask", 0);
     const int G = d["G"].cast<int>();
-    dim3 grid(gs_blocks((long long)a.B * a.H * a.W * a.C, G), G);
+    TORCH_CHECK(a.C % 4 == 0);
+    dim3 grid(gs_blocks((long long)a.B * a.H * a.W * (a.C / 4), G), G);
     mb::maxpool_bwd_kernel<<<grid, 256, 0, lstream()>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

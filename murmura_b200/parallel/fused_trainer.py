@@ -76,20 +76,24 @@ class CudaBackend:
         return t
 
     def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab: Optional[torch.Tensor] = None,
-             geom: Optional[cp.ConvGeom] = None) -> None:
+             geom: Optional[cp.ConvGeom] = None, warena: Optional[torch.Tensor] = None) -> None:
+        """``warena`` [groups, row] replaces the arena as the weight source (packed first-layer weights, indexed by group)."""
         d = {k: v for k, v in plan.items() if k != "ptab_shape"}
-        d.update(G=G, X=X.ptr(), x_gs=X.gs, Y=Y.ptr(), y_gs=Y.gs, arena=tr.live.data_ptr(), arena_gs=tr.stride,
-                 gmap=tr.gmap.data_ptr(), ones=self.ones.data_ptr())
+        arena = tr.live if warena is None else warena
+        d.update(G=G, X=X.ptr(), x_gs=X.gs, Y=Y.ptr(), y_gs=Y.gs, arena=arena.data_ptr(), arena_gs=int(arena.shape[1]),
+                 gmap=tr.gmap.data_ptr() if warena is None else 0, ones=self.ones.data_ptr())
         if R is not None:
             d.update(R=R.ptr(), r_gs=R.gs)
         self.launches += 1
+        if warena is not None:
+            row_tab = None                               # the packing kernel already resolved foreign rows
         if geom is not None and row_tab is None and getattr(tr, "use_tma", True):
-            key = (geom, plan["mode"], X.ptr(), Y.ptr(), plan["w_off"])
+            key = (geom, plan["mode"], X.ptr(), Y.ptr(), plan["w_off"], arena.data_ptr())
             if key not in self._tma:
                 from murmura_b200.ops.conv_launch import encode_tma
                 self._tma[key] = encode_tma(self.ext, plan["mode"], geom, x_ptr=X.ptr(), x_gs=X.gs, y_ptr=Y.ptr(), y_gs=Y.gs,
-                                            w_ptr=tr.live.data_ptr() + plan["w_off"] * 4, arena_stride=tr.stride,
-                                            slots=int(tr.live.shape[0]), groups=int(X.t.shape[0]))
+                                            w_ptr=arena.data_ptr() + plan["w_off"] * 4, arena_stride=int(arena.shape[1]),
+                                            slots=int(arena.shape[0]), groups=int(X.t.shape[0]))
             extra = self._tma[key]
             if extra is not None:
                 d.update(extra)
@@ -119,22 +123,38 @@ class EmuBackend:
     def _np(buf: Buf, g: int) -> np.ndarray:
         return buf.t[g].numpy()
 
-    def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab=None, geom=None) -> None:
+    def conv(self, tr: "FusedTrainer", plan: Dict, G: int, X: Buf, Y: Buf, R: Optional[Buf] = None, row_tab=None, geom=None, warena=None) -> None:
         for g in range(G):
-            row = tr.live[int(tr.gmap[g])].numpy()
+            row = tr.live[int(tr.gmap[g])].numpy() if warena is None else warena[g].numpy()
             cp.emulate(plan, self._np(X, g), self._np(Y, g), row, None if R is None else self._np(R, g))
         self.launches += 1
 
     # ---- layers.cu equivalents (tensor arguments instead of addresses) ----
     def gather(self, tr: "FusedTrainer", G: int, t: int) -> None:
+        """Mini-batch gather + im2col of the first layer + packing of its weights (``im2col_pack_kernel``)."""
+        import torch.nn.functional as F
+        f = tr.first
         for g in range(G):
             slot = int(tr.gmap[g])
             X, y = tr.shards[slot]
             idx = tr.perm[slot, t * tr.eb:(t + 1) * tr.eb]
-            xb = X.index_select(0, idx).reshape(tr.eb, tr.npix, tr.Csrc)
-            out = tr.xb.t[g].view(tr.eb, tr.npix, tr.Cdst)
-            out.zero_(); out[..., :tr.Csrc] = xb
+            xb = X.index_select(0, idx).reshape(tr.eb, f["IH"], f["IW"], f["Cin"]).permute(0, 3, 1, 2)
+            cols = F.unfold(xb, (f["KH"], f["KW"]), padding=f["pad"], stride=f["stride"])          # [eb, Cin·KH·KW, L], (c, kh, kw) order
+            L = cols.shape[-1]
+            cols = cols.view(tr.eb, f["Cin"], f["KH"] * f["KW"], L).permute(0, 3, 2, 1).reshape(tr.eb * L, f["Kreal"])
+            out = tr.xb.t[g].view(tr.eb * L, f["Kpad"])
+            out.zero_(); out[:, :f["Kreal"]] = cols
             tr.yb[g].copy_(y.index_select(0, idx))
+            row = tr.live[slot]
+            wp = tr.wpack[g]
+            wp.zero_()
+            wp[: f["Cout"] * f["Kpad"]].view(f["Cout"], f["Kpad"])[:, :f["Kreal"]] = row[f["w_off"]:f["w_off"] + f["Cout"] * f["Kreal"]].view(f["Cout"], f["Kreal"])
+            base, Cp = f["Cout"] * f["Kpad"], cp.ceil4(f["Cout"])
+            if f["bias_off"] >= 0:
+                wp[base: base + f["Cout"]] = row[f["bias_off"]:f["bias_off"] + f["Cout"]]
+            for j, key in enumerate(("bn_mean_off", "bn_var_off", "bn_gamma_off", "bn_beta_off")):
+                if f.get(key, -1) >= 0:
+                    wp[base + (j + 1) * Cp: base + (j + 1) * Cp + f["Cout"]] = row[f[key]:f[key] + f["Cout"]]
         tr.rng_step += 1
         self.launches += 1
 
@@ -248,7 +268,16 @@ class ConvOp:
         self.name, self.x, self.y, self.geom, self.w_off, self.bias_off = name, x, y, geom, w_off, bias_off
         self.relu, self.act, self.first = relu, act, first
         self.bn, self.res = bn, res                    # inference only: eval-mode BatchNorm (+residual) folded into the epilogue
-        self.pf = cp.plan_fprop(geom, aligned_weights=(w_off % 4 == 0))
+        if first:
+            # ``x`` is the im2col buffer [rows, Kpad]; fprop reads the per-step packed weights (rows of Kpad floats + bias),
+            # wgrad steps the real weights in the arena (rows of Kreal floats)
+            self.geom_f = cp.ConvGeom(B=geom.B, IH=1, IW=1, Cin=geom.Cin_pad, Cout=geom.Cout)
+            self.pf = cp.plan_fprop(self.geom_f)
+            self.f_bias_off = geom.Cout * geom.Cin_pad if bias_off >= 0 else -1
+        else:
+            self.geom_f = geom
+            self.pf = cp.plan_fprop(geom, aligned_weights=(w_off % 4 == 0))
+            self.f_bias_off = bias_off
         self.pd = None if first else cp.plan_dgrad(geom)
         self.pw = cp.plan_wgrad(geom, bias=bias_off >= 0)
         self.fused_out = relu or act != 0 or bn is not None or res is not None
@@ -269,21 +298,27 @@ class ConvOp:
     def fwd(self, tr: "FusedTrainer", G: int) -> None:
         p = dict(self.pf)
         split = 1 if self.fused_out else self._split(p, G, tr.target_ctas)
-        p.update(w_off=self.w_off, bias_off=self.bias_off, relu=int(self.relu), act=self.act, splitk=split)
+        p.update(w_off=0 if self.first else self.w_off, bias_off=self.f_bias_off, relu=int(self.relu), act=self.act, splitk=split)
         if self.bn is not None:
-            p.update(bn_mean_off=self.bn["running_mean"], bn_var_off=self.bn["running_var"], bn_gamma_off=self.bn["weight"],
-                     bn_beta_off=self.bn["bias"], eps=self.bn["eps"])
+            if self.first:                               # the packing kernel copied the statistics behind the packed weights
+                base, Cp = self.geom.Cout * self.geom.Cin_pad, cp.ceil4(self.geom.Cout)
+                p.update(bn_mean_off=base + Cp, bn_var_off=base + 2 * Cp, bn_gamma_off=base + 3 * Cp, bn_beta_off=base + 4 * Cp, eps=self.bn["eps"])
+            else:
+                p.update(bn_mean_off=self.bn["running_mean"], bn_var_off=self.bn["running_var"], bn_gamma_off=self.bn["weight"],
+                         bn_beta_off=self.bn["bias"], eps=self.bn["eps"])
         assert split == 1 or self.y.pooled
-        tr.be.conv(tr, p, G, self.x, self.y, R=self.res, row_tab=getattr(tr, "row_tab", None), geom=self.geom)
+        tr.be.conv(tr, p, G, self.x, self.y, R=self.res, row_tab=getattr(tr, "row_tab", None), geom=self.geom_f,
+                   warena=tr.wpack if self.first else None)
 
     def bwd(self, tr: "FusedTrainer", G: int, lr: float) -> None:
         dy = self.y.grad
         if self.pd is not None:
             p = dict(self.pd)
             mask = self.x.relu_fused
-            split = 1 if mask else self._split(p, G, tr.target_ctas)
-            p.update(w_off=self.w_off, splitk=split, accumulate=int(self.dgrad_accumulate or split > 1))
-            assert not (split > 1 and not self.dgrad_accumulate) or self.x.grad.pooled
+            strided = self.geom.stride > 1                  # parity-class launch: no split-K, classes may not cover every pixel
+            split = 1 if (mask or strided) else self._split(p, G, tr.target_ctas)
+            p.update(w_off=self.w_off, splitk=split, accumulate=int(self.dgrad_accumulate or split > 1 or strided))
+            assert not ((split > 1 or strided) and not self.dgrad_accumulate) or self.x.grad.pooled
             if mask:
                 p.update(rmode=2)
             tr.be.conv(tr, p, G, dy, self.x.grad, R=self.x if mask else None, geom=self.geom)
@@ -445,19 +480,34 @@ class _Builder:
 
     def conv(self, prefix: str, m: nn.Module, x: Buf, H: int, W: int, relu: bool = False, act: int = 0, first: bool = False,
              bn: Optional[Dict[str, Any]] = None, res: Optional[Buf] = None) -> Tuple[Buf, int, int]:
+        bias = self.off(prefix + ".bias") if m.bias is not None else -1
         if isinstance(m, nn.Conv2d):
             assert m.groups == 1 and m.dilation == (1, 1) and m.kernel_size[0] == m.kernel_size[1] and m.stride[0] == m.stride[1] \
                 and m.padding[0] == m.padding[1] and m.padding_mode == "zeros"
             g = cp.ConvGeom(B=self.B, IH=H, IW=W, Cin=m.in_channels, Cout=m.out_channels, KH=m.kernel_size[0], KW=m.kernel_size[1],
-                            stride=m.stride[0], pad=m.padding[0], Cin_pad=x.ld)
+                            stride=m.stride[0], pad=m.padding[0], Cin_pad=cp.ceil4(m.in_channels) if first else x.ld)
         else:
-            g = cp.ConvGeom(B=self.B, IH=1, IW=1, Cin=m.in_features, Cout=m.out_features, Cin_pad=x.ld)
-        assert x.ld >= g.Cin and (first or x.ld == g.Cin), f"{prefix}: input buffer has {x.ld} floats per pixel for {g.Cin} channels"
-        if not first and (self.off(prefix + ".weight") % 4 or g.wrow % 4):
+            g = cp.ConvGeom(B=self.B, IH=1, IW=1, Cin=m.in_features, Cout=m.out_features, Cin_pad=cp.ceil4(m.in_features) if first else x.ld)
+        if first:
+            # the gather kernel writes the im2col matrix of the batch: the layer becomes a GEMM over rows of Kpad floats
+            Kreal = g.KH * g.KW * g.Cin
+            Kpad = cp.ceil32(Kreal)
+            rows = self.B * g.OH * g.OW
+            xcol = self.buf("input.col", rows, Kreal, Kpad)
+            self.tr.xb = xcol
+            self.tr.first = dict(IH=g.IH, IW=g.IW, Cin=g.Cin, KH=g.KH, KW=g.KW, stride=g.stride, pad=g.pad, OH=g.OH, OW=g.OW, Kreal=Kreal,
+                                 Kpad=Kpad, Cout=g.Cout, w_off=self.off(prefix + ".weight"), bias_off=bias)
+            if bn is not None:
+                self.tr.first.update(bn_mean_off=bn["running_mean"], bn_var_off=bn["running_var"], bn_gamma_off=bn["weight"], bn_beta_off=bn["bias"])
+            gl = cp.ConvGeom(B=rows, IH=1, IW=1, Cin=Kreal, Cout=g.Cout, Cin_pad=Kpad)
+            y = self.buf(prefix + ".out", rows, g.Cout)
+            self.ops.append(ConvOp(prefix, xcol, y, gl, self.off(prefix + ".weight"), bias, relu=relu, act=act, first=True, bn=bn, res=res))
+            return y, g.OH, g.OW
+        assert x.ld == g.Cin, f"{prefix}: input buffer has {x.ld} floats per pixel for {g.Cin} channels"
+        if self.off(prefix + ".weight") % 4 or g.wrow % 4:
             raise _Unsupported(f"{prefix}: weights are not 16-byte aligned in the arena row")
         y = self.buf(prefix + ".out", self.B * g.OH * g.OW, g.Cout)
-        bias = self.off(prefix + ".bias") if m.bias is not None else -1
-        self.ops.append(ConvOp(prefix, x, y, g, self.off(prefix + ".weight"), bias, relu=relu, act=act, first=first, bn=bn, res=res))
+        self.ops.append(ConvOp(prefix, x, y, g, self.off(prefix + ".weight"), bias, relu=relu, act=act, first=False, bn=bn, res=res))
         return y, g.OH, g.OW
 
     def bn(self, prefix: str, m: nn.Module, x: Buf, res: Optional[Buf], relu: bool, p_drop: float = 0.0) -> Buf:
@@ -503,14 +553,10 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
     image = len(sample_shape) == 3
     if image:
         Cin, H, W = sample_shape                      # logical (C, H, W); shards are stored NHWC
-        tr.npix, tr.Csrc, tr.Cdst = H * W, Cin, cp.ceil4(Cin)
-        x0 = b.buf("input", B * H * W, Cin, tr.Cdst)
     else:
-        K = int(np.prod(sample_shape))
-        tr.npix, tr.Csrc, tr.Cdst = 1, K, cp.ceil4(K)
-        x0 = b.buf("input", B, K, tr.Cdst)
         H = W = 1
-    tr.xb = x0
+    x0 = None                                         # the first conv / linear layer creates the im2col input buffer (tr.xb)
+    tr.first = None
 
     def check_channels(*convs) -> bool:
         return all(c.in_channels % 4 == 0 for c in convs)
@@ -629,6 +675,25 @@ def build_program(tr: "FusedTrainer", model: nn.Module, B: int, sample_shape: Se
     return True
 
 
+
+def first_layer_args(tr, G: int, t: int, perm: torch.Tensor, x_tab: torch.Tensor, y_tab: torch.Tensor, row_tab: Optional[torch.Tensor] = None,
+                     rng: bool = False) -> Dict[str, Any]:
+    """Arguments of ``im2col_pack`` for a trainer / forward program ``tr`` (gather + im2col + first-layer weight packing)."""
+    f = tr.first
+    d = dict(G=G, x_tab=x_tab.data_ptr(), y_tab=y_tab.data_ptr(), perm=perm.data_ptr(), perm_ld=perm.shape[1], gmap=tr.gmap.data_ptr(),
+             xcol=tr.xb.ptr(), xcol_gs=tr.xb.gs, yb=tr.yb.data_ptr(), yb_gs=tr.yb.shape[1], t=t, eb=tr.eb,
+             arena=tr.live.data_ptr(), arena_gs=tr.stride, wmap=tr.gmap.data_ptr(), wpack=tr.wpack.data_ptr(), wpack_gs=tr.wpack.shape[1])
+    d.update({k: v for k, v in f.items()})
+    if row_tab is not None:
+        d.update(row_tab=row_tab.data_ptr())
+    if rng:
+        d.update(rng_step=tr.rng_step.data_ptr(), ticket=tr.ticket.data_ptr())
+    return d
+
+
+def wpack_row_floats(first: Dict[str, Any]) -> int:
+    return first["Cout"] * first["Kpad"] + 5 * cp.ceil4(first["Cout"])
+
 # =====================================================================================================================
 # the trainer
 # =====================================================================================================================
@@ -728,8 +793,8 @@ class FusedTrainer:
                 if op.pd is not None:
                     g = self._grad(op.x)
                     op.dgrad_accumulate = not first_write(op.x)
-                    if op.may_split_bwd(self.target_ctas) and not op.dgrad_accumulate:
-                        root(g).pooled = True
+                    if (op.may_split_bwd(self.target_ctas) or op.geom.stride > 1) and not op.dgrad_accumulate:
+                        root(g).pooled = True             # split-K slices / the parity classes of a strided dgrad add into zeros
             elif isinstance(op, BNOp):
                 self._grad(op.y); self._grad(op.x)
                 assert first_write(op.x), f"{op.name}: BatchNorm input has another gradient producer"
@@ -763,6 +828,7 @@ class FusedTrainer:
                 while r.base is not None:
                     r = r.base
                 b.t, b.gs, b.pooled = r.t, r.gs, r.pooled
+        self.wpack = torch.zeros(G, wpack_row_floats(self.first), device=dev)
         for op in self.bn_ops:
             op.save_mean = torch.zeros(G, op.x.C, device=dev)
             op.save_invstd = torch.zeros(G, op.x.C, device=dev)
@@ -785,10 +851,7 @@ class FusedTrainer:
     def _gather(self, G: int, t: int) -> None:
         if self.be.name == "emu":
             return self.be.gather(self, G, t)
-        self.be.call("gather_grouped", dict(G=G, x_tab=self.x_tab.data_ptr(), y_tab=self.y_tab.data_ptr(), perm=self.perm.data_ptr(),
-                                            perm_ld=self.perm.shape[1], gmap=self.gmap.data_ptr(), xb=self.xb.ptr(), xb_gs=self.xb.gs,
-                                            yb=self.yb.data_ptr(), yb_gs=self.yb.shape[1], rng_step=self.rng_step.data_ptr(),
-                                            ticket=self.ticket.data_ptr(), t=t, eb=self.eb, npix=self.npix, Csrc=self.Csrc, Cdst=self.Cdst))
+        self.be.call("im2col_pack", first_layer_args(self, G, t, self.perm, self.x_tab, self.y_tab, rng=True))
 
     def step(self, G: int, t: int, lr: float) -> None:
         if G <= 0:
@@ -908,13 +971,13 @@ class FusedForward:
         self.gmap = torch.arange(self.Gmax, dtype=torch.int32, device=dev)
         self.yb = torch.zeros(self.Gmax, self.eb, dtype=torch.int64, device=dev)
         self.stats = torch.zeros(self.Gmax, 8, device=dev)
+        self.wpack = torch.zeros(self.Gmax, wpack_row_floats(self.first), device=dev)
         self.workspace_bytes = sum(b.t.numel() * 4 for b in self.bufs)
 
     def load(self, G: int, x_tab: torch.Tensor, y_tab: torch.Tensor, perm: torch.Tensor, t: int) -> None:
-        """``xb[g] = X_{gmap[g]}[perm[gmap[g], t·rows : (t+1)·rows]]`` (+ labels) for the first ``G`` groups."""
-        self.be.call("gather_grouped", dict(G=G, x_tab=x_tab.data_ptr(), y_tab=y_tab.data_ptr(), perm=perm.data_ptr(), perm_ld=perm.shape[1],
-                                            gmap=self.gmap.data_ptr(), xb=self.xb.ptr(), xb_gs=self.xb.gs, yb=self.yb.data_ptr(),
-                                            yb_gs=self.yb.shape[1], t=t, eb=self.eb, npix=self.npix, Csrc=self.Csrc, Cdst=self.Cdst))
+        """Inputs of the first ``G`` groups: rows ``perm[gmap[g], t·rows : (t+1)·rows]`` of shard ``gmap[g]`` (im2col'ed for the first
+        layer) + labels, and the packed first-layer weights of the groups' weight rows (``row_tab`` or the arena slot)."""
+        self.be.call("im2col_pack", first_layer_args(self, G, t, perm, x_tab, y_tab, row_tab=self.row_tab))
 
     def forward(self, G: int) -> None:
         for op in self.ops:
