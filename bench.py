@@ -183,6 +183,7 @@ def run_ours(args):
     # ---- device-timed number (shards resident in HBM) -----------------------------------------
     net = make(stream_inputs=False)
     net.train(rounds=args.warmup, local_epochs=W["local_epochs"], lr=W["lr"])
+    net.reset_timers()
     launches0 = net.kernel_launches
     if rank == 0:
         sampler.start()
@@ -192,6 +193,15 @@ def run_ours(args):
     ms = _max_over_ranks(ms, device)
     final_acc = float(net.history["mean_accuracy"][-1])
     params = net.layout.P_float_real
+    phases = None
+    if net.opt.profile and net.timers["rounds"]:
+        r = net.timers["rounds"]
+        phases = {k: round(net.timers[k] / r, 3) for k in ("train_ms", "aggregate_ms", "eval_ms")}
+        fused = getattr(net, "fused", None)
+        phases["fused_train"] = fused is not None
+        if fused is not None:
+            phases["steps_per_round"] = fused.max_steps
+            phases["active_nodes_per_step"] = fused.active
     net.close()
 
     # ---- end-to-end number through the public API (pinned host shards → H2D every round, metrics D2H) ----
@@ -222,6 +232,8 @@ def run_ours(args):
                "e2e": {"value": args.steps / wall, "unit": "rounds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "timing": "wall clock around Network.train(rounds=K), barrier+synchronize both sides, max over ranks"},
                "gpu_launches": int(launches)}
+        if phases is not None:
+            out["phase_ms"] = phases
         print(json.dumps(out), flush=True)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

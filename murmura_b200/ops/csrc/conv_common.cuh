@@ -47,9 +47,28 @@ struct ConvGemmParams {
 // ---- epilogue of modes F / D: one accumulator row per thread (TMEM lane), 16 columns per tcgen05.ld -------------------------------
 // `grow` = global GEMM row of this thread (< 0: nothing to store).  All launch-invariant switches are hoisted out of the
 // element loops: with one warp per SM sub-partition every dependent constant load / branch is exposed latency.
+// Eval-mode BatchNorm of the output channels [n0, n0 + BN) as one scale / shift pair per column (call with the 128 epilogue
+// threads before the accumulator is ready; `ss` = 2·BN floats of shared memory).
+template <int BN>
+__device__ __forceinline__ void epilogue_prepare_bn(const ConvGemmParams& p, const float* __restrict__ row, int n0, int tid, float* ss) {
+    if (p.bn_mean_off < 0) return;
+    for (int i = tid; i < BN; i += 128) {
+        const int col = n0 + i;
+        float sc = 0.f, sh = 0.f;
+        if (col < p.N) {
+            const float g_ = p.bn_gamma_off >= 0 ? row[p.bn_gamma_off + col] : 1.f;
+            const float b_ = p.bn_beta_off >= 0 ? row[p.bn_beta_off + col] : 0.f;
+            sc = rsqrtf(row[p.bn_var_off + col] + p.eps) * g_;
+            sh = b_ - row[p.bn_mean_off + col] * sc;
+        }
+        ss[i] = sc; ss[BN + i] = sh;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const ConvGemmParams& p, uint32_t tmem_base, int warp, long long grow, int n0, int g,
-                                              int split, float* __restrict__ row, float* __restrict__ Yg) {
+                                              int split, float* __restrict__ row, float* __restrict__ Yg, const float* __restrict__ ss) {
     const int N = p.N, ldy = p.ldy;
     const float alpha = p.alpha;
     const bool rvalid = grow >= 0;
@@ -81,11 +100,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmParams& p, uint32_t 
                 const int col = cbase + i;
                 if (full || col < N) {
                     float x = f[i];
-                    if (bn) {
-                        const float g_ = p.bn_gamma_off >= 0 ? row[p.bn_gamma_off + col] : 1.f;
-                        const float b_ = p.bn_beta_off >= 0 ? row[p.bn_beta_off + col] : 0.f;
-                        x = (x - row[p.bn_mean_off + col]) * rsqrtf(row[p.bn_var_off + col] + p.eps) * g_ + b_;
-                    }
+                    if (bn) x = fmaf(x, ss[c0 + i], ss[BN + c0 + i]);
                     if (rrow) { if (mask) x = rrow[col] > 0.f ? x : 0.f; else x += rrow[col]; }
                     if (relu) x = fmaxf(x, 0.f);
                     else if (act2) x = (x > 20.f ? x : log1pf(__expf(x))) + 1.f;       // Dirichlet head: softplus + 1

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
     __shared__ __align__(8) uint64_t empty_bar[NS];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float bn_ss[2 * BN];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) CG_STAMP(0);
@@ -250,11 +251,12 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
         }
         // ================= epilogue: TMEM → registers → global =================
         if (tid == 0) CG_STAMP(3);
+        if (MODE != kModeW) epilogue_prepare_bn<BN>(p, row, n0, tid, bn_ss);
         mbar_wait_backoff(&accum_bar, 0);
         tc_fence_after();
         if (tid == 0) CG_STAMP(5);
         const int r = m0 + warp * 32 + lane;
-        if (MODE != kModeW) epilogue_rows<BN>(p, tmem_base, warp, r < p.M ? (long long)r : -1ll, n0, g, split, row, Yg);
+        if (MODE != kModeW) epilogue_rows<BN>(p, tmem_base, warp, r < p.M ? (long long)r : -1ll, n0, g, split, row, Yg, bn_ss);
         else epilogue_wgrad<BN>(p, tmem_base, warp, r, n0, row);
     } else if (lane == 0) {
         // ================= MMA issuer: 4 × (128 × BN × 8) tf32 MMAs per k-block =================

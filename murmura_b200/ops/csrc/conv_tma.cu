@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
     __shared__ __align__(8) uint64_t empty_bar[NS];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float bn_ss[2 * BN];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - g * p.splitk;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
     } else {
         // ================= epilogue =================
         float* row = p.arena + (long long)slot * p.arena_gs;
+        if (MODE != kModeW) epilogue_prepare_bn<BN>(p, row, n0, tid, bn_ss);
         if (nkb > 0) {
             mbar_wait_backoff(&accum_bar, 0);
             tc_fence_after();
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
                     if (y < P.RH && b < P.nB)
                         grow = ((long long)b * P.OPH + (y * P.osc + cls.py)) * P.OPW + (x * P.osc + cls.px);
                 }
-                epilogue_rows<BN>(p, tmem_base, warp, grow, n0, g, split, row, p.Y + (long long)g * p.y_gs);
+                epilogue_rows<BN>(p, tmem_base, warp, grow, n0, g, split, row, p.Y + (long long)g * p.y_gs, bn_ss);
             } else {
                 epilogue_wgrad<BN>(p, tmem_base, warp, (int)blockIdx.x * kCgBM + r, n0, row);
             }

@@ -89,32 +89,36 @@ struct Im2colArgs {
 };
 
 __global__ void __launch_bounds__(256) im2col_pack_kernel(Im2colArgs a) {
+    extern __shared__ int ktab[];                            // k → (kh << 16 | kw << 8 | c), −1 for the padding columns
     const int g = blockIdx.z, r = blockIdx.y;
     const int K4 = a.Kpad >> 2;
     if (r < a.eb) {
+        for (int k = threadIdx.x; k < a.Kpad; k += blockDim.x) {
+            int e = -1;
+            if (k < a.Kreal) { const int tap = k / a.Cin, c = k - tap * a.Cin; const int kh = tap / a.KW; e = (kh << 16) | ((tap - kh * a.KW) << 8) | c; }
+            ktab[k] = e;
+        }
+        __syncthreads();
         const int slot = a.gmap ? a.gmap[g] : g;
         const long long src = a.perm[(long long)slot * a.perm_ld + (long long)a.t * a.eb + r];
-        const float* in = reinterpret_cast<const float*>(a.x_tab[slot]) + src * (long long)a.IH * a.IW * a.Cin;
+        const float* __restrict__ in = reinterpret_cast<const float*>(a.x_tab[slot]) + src * (long long)a.IH * a.IW * a.Cin;
         const int P = a.OH * a.OW;
-        float* out = a.xcol + (long long)g * a.xcol_gs + (long long)r * P * a.Kpad;
-        const int total = P * K4;
-        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
-            const int pix = q / K4, k4 = (q - pix * K4) << 2;
+        float* __restrict__ out = a.xcol + (long long)g * a.xcol_gs + (long long)r * P * a.Kpad;
+        // a warp walks 32 consecutive k of one output pixel: coalesced 128-byte stores, image reads stay in L1
+        const int warps = (gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        for (int pix = wid; pix < P; pix += warps) {
             const int oh = pix / a.OW, ow = pix - oh * a.OW;
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k4 + j;
+            const int ih0 = oh * a.stride - a.pad, iw0 = ow * a.stride - a.pad;
+            float* orow = out + (long long)pix * a.Kpad;
+            for (int k = lane; k < a.Kpad; k += 32) {
+                const int e = ktab[k];
                 float x = 0.f;
-                if (k < a.Kreal) {
-                    const int tap = k / a.Cin, c = k - tap * a.Cin;
-                    const int kh = tap / a.KW, kw = tap - kh * a.KW;
-                    const int ih = oh * a.stride + kh - a.pad, iw = ow * a.stride + kw - a.pad;
-                    if (ih >= 0 && ih < a.IH && iw >= 0 && iw < a.IW) x = in[((long long)ih * a.IW + iw) * a.Cin + c];
+                if (e >= 0) {
+                    const int ih = ih0 + (e >> 16), iw = iw0 + ((e >> 8) & 255);
+                    if (ih >= 0 && ih < a.IH && iw >= 0 && iw < a.IW) x = in[((long long)ih * a.IW + iw) * a.Cin + (e & 255)];
                 }
-                v[j] = x;
+                orow[k] = x;
             }
-            *reinterpret_cast<float4*>(out + (long long)pix * a.Kpad + k4) = make_float4(v[0], v[1], v[2], v[3]);
         }
         if (blockIdx.x == 0 && threadIdx.x == 0)
             a.yb[(long long)g * a.yb_gs + r] = reinterpret_cast<const long long*>(a.y_tab[slot])[src];
@@ -695,9 +699,10 @@ void im2col_pack(py::dict d) {
     a.wpack = lptr<float>(d, "wpack"); a.wpack_gs = lget<int64_t>(d, "wpack_gs", 0); a.Cout = lget<int>(d, "Cout", 0);
     const int G = d["G"].cast<int>();
     TORCH_CHECK(G >= 1 && a.eb >= 1 && a.Kpad % 4 == 0 && a.Kpad >= a.Kreal && (a.rng_step == nullptr || a.ticket != nullptr));
-    const long long work = (long long)a.OH * a.OW * (a.Kpad / 4);
-    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(32, (work + 255) / 256)), (unsigned)(a.eb + (a.wpack ? 1 : 0)), (unsigned)G);
-    mb::im2col_pack_kernel<<<grid, 256, 0, lstream()>>>(a);
+    TORCH_CHECK(a.Cin < 256 && a.KW < 256 && a.KH < 256 && a.Kpad * 4 <= 48 * 1024, "im2col_pack: first-layer geometry out of range");
+    const long long pix = (long long)a.OH * a.OW;                          // 8 warps per block, one output pixel per warp pass
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(16, (pix + 7) / 8)), (unsigned)(a.eb + (a.wpack ? 1 : 0)), (unsigned)G);
+    mb::im2col_pack_kernel<<<grid, 256, a.Kpad * sizeof(int), lstream()>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

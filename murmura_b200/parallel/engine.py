@@ -1555,6 +1555,12 @@ class B200Network:
     # =========================================================================================
     # statistics / checkpoint / teardown
     # =========================================================================================
+    def reset_timers(self) -> None:
+        """Forget the per-phase timings collected so far (benchmarks call this after their warm-up rounds)."""
+        for k in ("train_ms", "aggregate_ms", "eval_ms", "rounds", "hbm_bytes", "nvlink_bytes"):
+            if k in self.timers:
+                self.timers[k] = 0.0
+
     def get_node_statistics(self) -> Dict[int, Dict[str, Any]]:
         out: Dict[int, Dict[str, Any]] = {}
         log = torch.stack(self._stat_log).cpu().numpy() if self._stat_log else np.zeros((0, max(self.V, 1), 4))

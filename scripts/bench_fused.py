@@ -21,7 +21,7 @@ MODELS = {"resnet18": (lambda: ResNet18(10), (3, 32, 32), 64, False), "femnist":
           "har": (lambda: EvidentialHARClassifier(), (561,), 32, True)}
 
 
-def build(name, G, steps, side):
+def build(name, G, steps, side, target_ctas=148):
     factory, shape, batch, evid = MODELS[name]
     dev = torch.device("cuda", 0)
     probe = factory()
@@ -36,7 +36,8 @@ def build(name, G, steps, side):
         n = batch * steps
         x = torch.randn(n, *shape, device=dev)
         shards.append((x.permute(0, 2, 3, 1).contiguous() if len(shape) == 3 else x, torch.randint(0, 6, (n,), device=dev)))
-    tr = FusedTrainer(models[0], layout, live, ints if layout.Pi else None, shards, [steps] * G, batch, shape, evidential=evid, side_stream=side)
+    tr = FusedTrainer(models[0], layout, live, ints if layout.Pi else None, shards, [steps] * G, batch, shape, evidential=evid, side_stream=side,
+                      target_ctas=target_ctas)
     assert tr.supported
     tr._models = models
     return tr
@@ -66,12 +67,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/bench_fused.json")
     ap.add_argument("--model", default="resnet18")
+    ap.add_argument("--target-ctas", type=int, default=148)
+    ap.add_argument("--quick", action="store_true", help="graph timings only (no eager per-launch pass)")
     args = ap.parse_args()
     out = {"model": args.model, "runs": []}
     for G in (1, 8):
         for side in (False, True):
             steps = 8
-            tr = build(args.model, G, steps, side)
+            tr = build(args.model, G, steps, side, args.target_ctas)
             tr.refresh_permutations(1)
             tr._capture(0.01)
             for _ in range(3):
@@ -86,7 +89,7 @@ def main():
             us_step = a.elapsed_time(b) * 1e3 / (reps * steps)
             run = {"G": G, "side_stream": side, "us_per_step_graph": round(us_step, 1), "launches_per_step": len(tr.ops) * 2 + 1,
                    "workspace_mb": round(tr.workspace_bytes / 2 ** 20, 1), "finite": bool(torch.isfinite(tr.live).all())}
-            if not side:
+            if not side and not args.quick:
                 rows = per_op(tr, G)
                 run["eager_sum_us"] = round(sum(t for _, t in rows), 1)
                 agg = {}

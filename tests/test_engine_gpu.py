@@ -192,13 +192,22 @@ def test_graphs_match_eager_and_simulation_statistically():
     accs = {}
     data = {"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}}
     for graphs in (True, False):
-        cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, b200={"cuda_graphs": graphs, "streams": 4}, data=data)
+        cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, b200={"cuda_graphs": graphs, "streams": 4, "fused_train": False},
+                   data=data)
         net, _, _ = _build(cfg)
         try:
             accs[graphs] = net.train(rounds=8, lr=0.05)["mean_accuracy"]
         finally:
             net.close()
     assert accs[True] == accs[False]            # same RNG streams, same kernels: CUDA graphs on 4 streams are bit-identical to eager
+    cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, data=data)        # default: the fused tcgen05 program
+    net, _, _ = _build(cfg)
+    try:
+        accs["fused"] = net.train(rounds=8, lr=0.05)["mean_accuracy"]
+        assert getattr(net, "fused", None) is not None and net.fused.be.tma_launches > 0
+    finally:
+        net.close()
+    assert abs(accs["fused"][-1] - accs[True][-1]) < 0.12 and accs["fused"][-1] > 0.6, accs
     sim_cfg = _cfg("fedavg", n=4, topo={"type": "fully", "num_nodes": 4}, data=data, backend="simulation")
     adapter = build_dataset_adapter(sim_cfg); mf = build_model_factory(sim_cfg)
     torch.manual_seed(3)
@@ -364,7 +373,7 @@ def test_split_backward_gradients_match_autograd_eager_and_graph():
 
 @pytest.mark.parametrize("split", [True, False, "auto"])
 def test_training_with_split_backward_modes(split):
-    cfg = _cfg("fedavg", n=4, topo={"type": "ring", "num_nodes": 4}, rounds=3, b200={"split_backward": split},
+    cfg = _cfg("fedavg", n=4, topo={"type": "ring", "num_nodes": 4}, rounds=3, b200={"split_backward": split, "fused_train": False},
                data={"adapter": "synthetic.mnist", "params": {"samples_per_node": 96, "partition_method": "iid"}})
     net, _, _ = _build(cfg)
     try:

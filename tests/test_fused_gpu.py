@@ -22,8 +22,6 @@ def _classes(m):
 
 def _setup(factory, shape, ns, batch, steps, evidential=False, side=False, seed=0):
     torch.manual_seed(seed)
-    from murmura_b200 import ops
-    ops.set_fused_bn(False)                                   # the autograd reference uses stock BatchNorm
     probe = factory()
     layout = StateLayout.from_model(probe, channels_last=True)
     S = len(ns)
