@@ -51,3 +51,11 @@ def mlp(input_dim: int = 784, hidden: int = 200, num_classes: int = 10):
     """Stock 2-layer MLP for BASELINE config 1 (plain torch.nn, nothing from this repo)."""
     import torch.nn as nn
     return nn.Sequential(nn.Flatten(), nn.Linear(input_dim, hidden), nn.ReLU(), nn.Linear(hidden, num_classes))
+
+
+def cifar_cnn(num_classes: int = 10):
+    """Stock small CIFAR-10 CNN of BASELINE configs 3 / 4: conv3(3→32)-conv3(32→64)-pool-conv3(64→128)-pool-fc256-fc (plain torch.nn)."""
+    import torch.nn as nn
+    return nn.Sequential(nn.Conv2d(3, 32, 3, padding=1), nn.ReLU(), nn.Conv2d(32, 64, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+                         nn.Conv2d(64, 128, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(), nn.Linear(128 * 8 * 8, 256), nn.ReLU(),
+                         nn.Linear(256, num_classes))

@@ -3,7 +3,10 @@
 8-node fully-connected FedAvg, ResNet-18 (11.19 M params), CIFAR-10-shaped synthetic non-IID shards
 (Dirichlet α=0.5, 512 samples/node, batch 64, 1 local epoch, lr 0.01, evaluation every round).
 
-    python bench.py --gpus N --steps K --warmup W [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference|nccl] [--config 2|3|4|5]
+
+``--impl nccl`` is the comparison baseline BASELINE.json names: the same engine and training, but the neighbour exchange goes
+through ``torch.distributed`` NCCL and the aggregation through stock PyTorch ops (``parallel/nccl_baseline.py``).
 
 One "step" = one complete federated round (local SGD over every node's shard + neighbour exchange +
 aggregation + evaluation of every node).  The 8 nodes are placed on N GPUs (8/N virtual nodes per GPU),
@@ -27,8 +30,40 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = {"nodes": 8, "samples_per_node": 512, "batch": 64, "local_epochs": 1, "lr": 0.01, "alpha": 0.5, "seed": 42}
 METRIC = "fl_rounds_per_sec"
+
+# BASELINE.json configs 2-5 (config 1 is the CPU simulation backend: scripts/cpu_config1.py).  The flagship (default) is 2.
+CONFIGS = {
+    2: {"yaml": "resnet18_fully_fedavg_b200.yaml", "model": "resnet18", "ref_model": ("baseline.ref_workloads.resnet18", {"num_classes": 10}),
+        "ref_data": "cifar10"},
+    3: {"yaml": "cnn_kregular_krum_gaussian_b200.yaml", "model": "cifar_cnn", "ref_model": ("baseline.ref_workloads.cifar_cnn", {"num_classes": 10}),
+        "ref_data": "cifar10"},
+    4: {"yaml": "er16_sketchguard_fp8_directed_b200.yaml", "model": "cifar_cnn", "ref_model": ("baseline.ref_workloads.cifar_cnn", {"num_classes": 10}),
+        "ref_data": "cifar10"},
+    5: {"yaml": "mobility32_ubar_dmtt_liar_b200.yaml", "model": "leaf_femnist_cnn", "ref_model": None, "ref_data": "femnist"},
+}
+
+
+def load_bench_config(idx: int):
+    """The bundled YAML of BASELINE config ``idx`` (murmura_b200/examples/configs)."""
+    from murmura_b200.config import load_config
+    path = os.path.join(ROOT, "murmura_b200", "examples", "configs", CONFIGS[idx]["yaml"])
+    return load_config(path)
+
+
+def describe(cfg, idx: int, world: int):
+    """The ``config`` block of the JSON line — identical for every arm (implementation details go to ``impl_detail``)."""
+    d = cfg.data.params
+    atk = cfg.attack
+    return {"baseline_config": idx, "model": CONFIGS[idx]["model"], "nodes": cfg.topology.num_nodes,
+            "topology": cfg.topology.type if cfg.mobility is None else "mobility G^t",
+            "aggregation": cfg.aggregation.algorithm + ("+dmtt" if cfg.dmtt is not None else ""),
+            "attack": f"{atk.type} {atk.percentage:g}" if atk.enabled else "none",
+            "global_batch": cfg.training.batch_size * cfg.topology.num_nodes, "samples_per_node": d.get("samples_per_node"),
+            "partition": f"{d.get('partition_method', 'dirichlet')} alpha={d.get('alpha', 0.5)}", "batch_size": cfg.training.batch_size,
+            "local_epochs": cfg.training.local_epochs, "seq_len": None, "lr": cfg.training.lr, "eval_every": 1,
+            "parallelism": f"{cfg.topology.num_nodes} federated nodes over {world} GPU(s) of one box",
+            "l2": "flushed between rounds (256 MiB write), one CUDA-event pair per round"}
 
 
 class ClockSampler:
@@ -150,66 +185,82 @@ def _b200_overrides(args):
     return out
 
 
+def _criterion(cfg):
+    from murmura_b200.utils.factories import build_criterion
+    return build_criterion(cfg)
+
+
 def run_ours(args):
+    """``--impl ours`` (fused kernels, in-kernel P2P / NVLS exchange) and ``--impl nccl`` (same engine, NCCL + PyTorch exchange/aggregation)."""
     import torch
     from murmura_b200 import Network
-    from murmura_b200.config import Config
     from murmura_b200.parallel.engine import init_distributed
     from murmura_b200.utils.factories import build_aggregator_factory, build_dataset_adapter, build_model_factory
+    from murmura_b200.utils.seed import set_seed
 
     rank, world, local_rank = init_distributed()
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    W = WORKLOAD
+    transport = "nccl" if args.impl == "nccl" else args.transport
 
-    def make(stream_inputs: bool):
-        cfg = Config(**{
-            "experiment": {"name": "bench-resnet18-fully8-fedavg", "rounds": args.steps + args.warmup, "seed": W["seed"]},
-            "topology": {"type": "fully", "num_nodes": W["nodes"]},
-            "aggregation": {"algorithm": "fedavg"},
-            "training": {"batch_size": W["batch"], "lr": W["lr"], "local_epochs": W["local_epochs"]},
-            "data": {"adapter": "synthetic.cifar10", "params": {"samples_per_node": W["samples_per_node"],
-                                                                "partition_method": "dirichlet", "alpha": W["alpha"]}},
-            "model": {"factory": "models.resnet18", "params": {"num_classes": 10}},
-            "backend": "b200", "b200": {"stream_inputs": stream_inputs, "streams": 8, "transport": args.transport, **_b200_overrides(args)},
-        })
+    def make(stream_inputs: bool, profile: bool = False):
+        cfg = load_bench_config(args.config)
+        cfg.backend = "b200"
+        cfg.experiment.rounds = args.steps + args.warmup
+        over = {"stream_inputs": stream_inputs, "transport": transport, "profile": profile, **_b200_overrides(args)}
+        for k, v in over.items():
+            setattr(cfg.b200, k, v)
+        set_seed(cfg.experiment.seed)
         adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
-        return Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf), device=device)
+        crit, evid = _criterion(cfg)
+        import contextlib, io
+        with (contextlib.redirect_stdout(io.StringIO()) if rank else contextlib.nullcontext()):
+            net = Network.from_config(cfg, mf, adapter, build_aggregator_factory(cfg, mf), device=device, criterion=crit, evidential=evid)
+        return net, cfg
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     flush = lambda: flush_buf.fill_(1)
     sampler = ClockSampler(local_rank, str(getattr(torch.cuda.get_device_properties(device), 'uuid', '') or ''))
 
     # ---- device-timed number (shards resident in HBM) -----------------------------------------
-    net = make(stream_inputs=False)
-    net.train(rounds=args.warmup, local_epochs=W["local_epochs"], lr=W["lr"])
-    net.reset_timers()
+    net, cfg = make(stream_inputs=False)
+    T = cfg.training
+    net.train(rounds=args.warmup, local_epochs=T.local_epochs, lr=T.lr)
     launches0 = net.kernel_launches
     if rank == 0:
         sampler.start()
-    ms = _timed_rounds(lambda: net.train(rounds=1, local_epochs=W["local_epochs"], lr=W["lr"]), args.steps, device, flush)
+    ms = _timed_rounds(lambda: net.train(rounds=1, local_epochs=T.local_epochs, lr=T.lr), args.steps, device, flush)
     clocks = sampler.stop() if rank == 0 else None
     launches = net.kernel_launches - launches0
     ms = _max_over_ranks(ms, device)
     final_acc = float(net.history["mean_accuracy"][-1])
     params = net.layout.P_float_real
-    phases = None
-    if net.opt.profile and net.timers["rounds"]:
-        r = net.timers["rounds"]
-        phases = {k: round(net.timers[k] / r, 3) for k in ("train_ms", "aggregate_ms", "eval_ms")}
-        fused = getattr(net, "fused", None)
-        phases["fused_train"] = fused is not None
-        if fused is not None:
-            phases["steps_per_round"] = fused.max_steps
-            phases["active_nodes_per_step"] = fused.active
+    fused = getattr(net, "fused", None)
+    detail = {"transport": net.opt.transport, "fused_train": fused is not None, "nodes_per_gpu": net.V, "params_per_node": params,
+              "tma_conv_launches_per_round": (fused.be.tma_launches if fused is not None else 0)}
+    # ---- phase split + roofline of the exchange+aggregate path (extra profiled rounds, outside the timed region) ----------
+    net.opt.profile = True
+    net.reset_timers()
+    net.train(rounds=5, local_epochs=T.local_epochs, lr=T.lr)
+    t = dict(net.timers)
+    r = max(t["rounds"], 1)
+    agg_ms = _max_over_ranks(t["aggregate_ms"] / r, device)
+    peaks = _peaks()
+    hbm_gbs = t.get("hbm_bytes", 0.0) / r / max(agg_ms, 1e-6) / 1e6
+    nvl_gbs = t.get("nvlink_bytes", 0.0) / r / max(agg_ms, 1e-6) / 1e6
+    phases = {"train_ms": round(_max_over_ranks(t["train_ms"] / r, device), 3), "aggregate_ms": round(agg_ms, 3),
+              "eval_ms": round(_max_over_ranks(t["eval_ms"] / r, device), 3)}
+    exch = {"ms_per_round": round(agg_ms, 4), "hbm_gbs": round(hbm_gbs, 1), "nvlink_gbs": round(nvl_gbs, 1),
+            "roofline_frac": round(max(hbm_gbs / peaks["hbm_gbs"], nvl_gbs / peaks["nvlink_gbs"]), 3),
+            "of": f"measured copy bandwidth {peaks['hbm_gbs']:.0f} GB/s (HBM) / {peaks['nvlink_gbs']:.0f} GB/s (NVLink peer), algorithmic bytes of rank 0"}
     net.close()
 
     # ---- end-to-end number through the public API (pinned host shards → H2D every round, metrics D2H) ----
-    net = make(stream_inputs=True)
-    net.train(rounds=args.warmup, local_epochs=W["local_epochs"], lr=W["lr"])
+    net, cfg = make(stream_inputs=True)
+    net.train(rounds=args.warmup, local_epochs=T.local_epochs, lr=T.lr)
     _barrier(); torch.cuda.synchronize(device)
     t0 = time.perf_counter()
-    net.train(rounds=args.steps, local_epochs=W["local_epochs"], lr=W["lr"])
+    net.train(rounds=args.steps, local_epochs=T.local_epochs, lr=T.lr)
     torch.cuda.synchronize(device); _barrier()
     wall = _max_over_ranks(time.perf_counter() - t0, device)
     h2d = _max_over_ranks(float(net.h2d_bytes_per_round), device)
@@ -220,33 +271,38 @@ def run_ours(args):
         value = args.steps / (ms / 1e3)
         out = {"metric": METRIC, "value": value, "unit": "rounds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "fp32 (cuDNN TF32 conv math = reference default)", "data": "synthetic", "impl": "ours",
-               "final_acc": final_acc,
-               "config": {"model": "resnet18 (11,191,242 float state elems)", "nodes": W["nodes"], "topology": "fully-connected",
-                          "aggregation": "fedavg", "global_batch": W["batch"] * W["nodes"], "samples_per_node": W["samples_per_node"],
-                          "batch_size": W["batch"], "local_epochs": W["local_epochs"], "seq_len": None, "lr": W["lr"],
-                          "parallelism": f"{W['nodes']} federated nodes on {world} GPU(s) ({W['nodes'] // world}/GPU), fused exchange+aggregate ({args.transport})",
-                          "l2": "flushed between rounds (256 MiB write), one CUDA-event pair per round",
-                          "params_per_node": params},
-               "clocks": clocks,
+               "dtype": "fp32 parameters, TF32 tensor-core math (tcgen05 kind::tf32; the reference's cuDNN default)", "data": "synthetic",
+               "impl": args.impl, "final_acc": final_acc, "config": describe(cfg, args.config, world), "clocks": clocks,
                "e2e": {"value": args.steps / wall, "unit": "rounds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "timing": "wall clock around Network.train(rounds=K), barrier+synchronize both sides, max over ranks"},
-               "gpu_launches": int(launches)}
-        if phases is not None:
-            out["phase_ms"] = phases
+               "gpu_launches": int(launches), "phase_ms": phases, "exchange_aggregate": exch, "roofline_frac": exch["roofline_frac"],
+               "impl_detail": detail}
         print(json.dumps(out), flush=True)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
 
 
+def _peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm_gbs": float(p["hbm_gbs"]), "nvlink_gbs": 770.0}
+    except Exception:  # noqa: BLE001 - the profiling recipe's stated fallback
+        return {"hbm_gbs": 6650.0, "nvlink_gbs": 770.0}
+
+
 def run_reference(args):
     """UNMODIFIED reference (baseline/_ref) through its own public API and stock simulation code path."""
     rank, world, local_rank = _dist_env()
     ref_root = os.path.join(ROOT, "baseline", "_ref")
+    reason = None
     if not os.path.isdir(os.path.join(ref_root, "murmura")):
+        reason = "baseline/_ref/murmura not installed (see DESIGN.md)"
+    elif CONFIGS[args.config]["ref_model"] is None:
+        reason = "config 5 needs the reference's distributed backend (wall-clock rounds of 120 s by construction)"
+    if reason:
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/murmura not installed (see DESIGN.md)"}))
+            print(json.dumps({"impl": "reference", "unavailable": reason}))
         return
     import torch
     if world > 1:
@@ -254,6 +310,7 @@ def run_reference(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
+    ours = load_bench_config(args.config)                       # only read for the workload description (no engine code runs)
     out = None
     if rank == 0:       # the reference has no multi-GPU path (every node uses get_device() → cuda:0); other ranks idle
         sys.path.insert(0, ref_root)
@@ -263,23 +320,33 @@ def run_reference(args):
         from murmura.utils.factories import build_aggregator_factory, build_dataset_adapter, build_model_factory
         from murmura.utils.seed import set_seed
         assert os.path.realpath(murmura.__file__).startswith(os.path.realpath(ref_root))
-        W = WORKLOAD
+        dp = ours.data.params
+        ref_model, ref_params = CONFIGS[args.config]["ref_model"]
+        topo = {"type": ours.topology.type, "num_nodes": ours.topology.num_nodes, "seed": ours.topology.seed}
+        if ours.topology.p is not None:
+            topo["p"] = ours.topology.p
+        if ours.topology.k is not None:
+            topo["k"] = ours.topology.k
         cfg = Config(**{
-            "experiment": {"name": "bench-reference", "rounds": args.steps + args.warmup, "seed": W["seed"]},
-            "topology": {"type": "fully", "num_nodes": W["nodes"]},
-            "aggregation": {"algorithm": "fedavg"},
-            "training": {"batch_size": W["batch"], "lr": W["lr"], "local_epochs": W["local_epochs"]},
+            "experiment": {"name": "bench-reference", "rounds": args.steps + args.warmup, "seed": ours.experiment.seed},
+            "topology": topo,
+            "aggregation": {"algorithm": ours.aggregation.algorithm, "params": dict(ours.aggregation.params)},
+            "attack": {"enabled": ours.attack.enabled, "type": ours.attack.type, "percentage": ours.attack.percentage, "params": dict(ours.attack.params)},
+            "training": {"batch_size": ours.training.batch_size, "lr": ours.training.lr, "local_epochs": ours.training.local_epochs},
             "data": {"adapter": "baseline.ref_workloads.SyntheticRefAdapter",
-                     "params": {"name": "cifar10", "num_nodes": W["nodes"], "samples_per_node": W["samples_per_node"],
-                                "alpha": W["alpha"], "seed": W["seed"]}},
-            "model": {"factory": "baseline.ref_workloads.resnet18", "params": {"num_classes": 10}},
+                     "params": {"name": CONFIGS[args.config]["ref_data"], "num_nodes": ours.topology.num_nodes,
+                                "samples_per_node": dp.get("samples_per_node", 512), "alpha": dp.get("alpha", 0.5), "seed": ours.experiment.seed}},
+            "model": {"factory": ref_model, "params": ref_params},
         })
-        set_seed(W["seed"])
+        T = cfg.training
+        set_seed(cfg.experiment.seed)
         adapter = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
         net = Network.from_config(config=cfg, model_factory=mf, dataset_adapter=adapter,
                                   aggregator_factory=build_aggregator_factory(cfg, mf, device), device=device)
-        shard_bytes = sum(len(p) for p in adapter.get_client_partitions()) * (3 * 32 * 32 * 4 + 8)
-        net.train(rounds=args.warmup, local_epochs=W["local_epochs"], lr=W["lr"])
+        sample_bytes = int(torch.tensor(ours_sample_shape(CONFIGS[args.config]["ref_data"])).prod()) * 4 + 8
+        shard_bytes = sum(len(p) for p in adapter.get_client_partitions()) * sample_bytes
+        model_bytes = sum(v.numel() * v.element_size() for v in mf().state_dict().values())
+        net.train(rounds=args.warmup, local_epochs=T.local_epochs, lr=T.lr)
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
         sampler = ClockSampler(local_rank, str(getattr(torch.cuda.get_device_properties(device), 'uuid', '') or '')); sampler.start()
         torch.cuda.synchronize(device)
@@ -288,26 +355,24 @@ def run_reference(args):
         for _ in range(args.steps):
             flush_buf.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); net.train(rounds=1, local_epochs=W["local_epochs"], lr=W["lr"]); b.record()
+            a.record(); net.train(rounds=1, local_epochs=T.local_epochs, lr=T.lr); b.record()
             pairs.append((a, b))
         torch.cuda.synchronize(device)
         wall = time.perf_counter() - t0
         ms = sum(a.elapsed_time(b) for a, b in pairs)
         clocks = sampler.stop()
+        N = ours.topology.num_nodes
         out = {"metric": METRIC, "value": args.steps / (ms / 1e3), "unit": "rounds/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-               "vs_baseline": None, "dtype": "fp32 (cuDNN TF32 conv math, torch defaults)", "data": "synthetic", "impl": "reference",
-               "final_acc": float(net.history["mean_accuracy"][-1]),
-               "config": {"model": "torchvision resnet18(num_classes=10)", "nodes": W["nodes"], "topology": "fully-connected",
-                          "aggregation": "fedavg", "global_batch": W["batch"] * W["nodes"], "samples_per_node": W["samples_per_node"],
-                          "batch_size": W["batch"], "local_epochs": W["local_epochs"], "seq_len": None, "lr": W["lr"],
-                          "parallelism": "reference simulation backend: sequential nodes on cuda:0 (it has no multi-GPU path); "
-                                         "ranks > 0 idle", "l2": "flushed between rounds (256 MiB write), one CUDA-event pair per round"},
+               "vs_baseline": None, "dtype": "fp32 parameters, TF32 tensor-core math (cuDNN / cuBLAS torch defaults)", "data": "synthetic",
+               "impl": "reference", "final_acc": float(net.history["mean_accuracy"][-1]), "config": describe(ours, args.config, world),
                "clocks": clocks,
                "e2e": {"value": args.steps / wall, "unit": "rounds/s", "h2d_bytes_per_step": int(shard_bytes * 2),
-                       "d2h_bytes_per_step": int(2 * 8 * 11_200_000 * 4),
+                       "d2h_bytes_per_step": int(2 * N * model_bytes),
                        "timing": "wall clock; the reference's DataLoader copies every batch H2D and get_state() copies every model D2H"},
-               "gpu_launches": 0}
+               "gpu_launches": 0,
+               "impl_detail": {"path": "reference simulation backend: sequential nodes on cuda:0 (it has no multi-GPU path); ranks > 0 idle",
+                               "model": ref_model}}
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
@@ -315,15 +380,20 @@ def run_reference(args):
         print(json.dumps(out), flush=True)
 
 
+def ours_sample_shape(name: str):
+    return {"cifar10": (3, 32, 32), "femnist": (1, 28, 28), "mnist": (784,)}[name]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "nccl"], default="ours")
+    ap.add_argument("--config", type=int, choices=sorted(CONFIGS), default=2, help="BASELINE.json config (default 2 = the flagship)")
     ap.add_argument("--b200", nargs="*", default=[], help="extra b200 engine options as key=value (ablations)")
-    ap.add_argument("--transport", choices=["p2p", "nvls", "nccl"], default="p2p",
-                    help="p2p: in-kernel peer loads (default); nvls: full-mesh FedAvg through multimem.ld_reduce; nccl: baseline")
+    ap.add_argument("--transport", choices=["auto", "p2p", "nvls"], default="auto",
+                    help="auto: NVLS multimem reduce for full-mesh FedAvg over several GPUs, in-kernel peer loads otherwise")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -98,9 +98,10 @@ class ModelConfig(BaseModel):
 class B200Config(BaseModel):
     """Blackwell engine knobs (new; all optional)."""
     gpus: Optional[int] = Field(default=None, description="GPUs to use; default WORLD_SIZE or 1")
-    transport: Literal["p2p", "nvls", "nccl"] = Field(
-        default="p2p", description="p2p = in-kernel peer loads (product); nvls = multimem "
-        "reduce for full-mesh FedAvg; nccl = baseline send/recv + PyTorch aggregation")
+    transport: Literal["auto", "p2p", "nvls", "nccl"] = Field(
+        default="auto", description="p2p = in-kernel peer loads; nvls = multimem.ld_reduce (in-switch sum) for full-mesh FedAvg; "
+        "auto = nvls whenever the round is a full-mesh FedAvg over several GPUs, p2p otherwise; nccl = baseline: NCCL exchange + "
+        "PyTorch aggregation")
     cuda_graphs: bool = Field(default=True, description="capture per-node train/eval steps in CUDA graphs")
     compute_dtype: Literal["fp32", "tf32", "bf16"] = Field(
         default="fp32", description="matmul/conv math mode for local training (params stay fp32)")

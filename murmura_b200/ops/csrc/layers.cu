@@ -89,13 +89,13 @@ struct Im2colArgs {
 };
 
 __global__ void __launch_bounds__(256) im2col_pack_kernel(Im2colArgs a) {
-    extern __shared__ int ktab[];                            // k → (kh << 16 | kw << 8 | c), −1 for the padding columns
+    extern __shared__ int ktab[];                            // k → (kh << 24 | kw << 16 | c), −1 for the padding columns
     const int g = blockIdx.z, r = blockIdx.y;
     const int K4 = a.Kpad >> 2;
     if (r < a.eb) {
         for (int k = threadIdx.x; k < a.Kpad; k += blockDim.x) {
             int e = -1;
-            if (k < a.Kreal) { const int tap = k / a.Cin, c = k - tap * a.Cin; const int kh = tap / a.KW; e = (kh << 16) | ((tap - kh * a.KW) << 8) | c; }
+            if (k < a.Kreal) { const int tap = k / a.Cin, c = k - tap * a.Cin; const int kh = tap / a.KW; e = (kh << 24) | ((tap - kh * a.KW) << 16) | c; }
             ktab[k] = e;
         }
         __syncthreads();
@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(256) im2col_pack_kernel(Im2colArgs a) {
                 const int e = ktab[k];
                 float x = 0.f;
                 if (e >= 0) {
-                    const int ih = ih0 + (e >> 16), iw = iw0 + ((e >> 8) & 255);
-                    if (ih >= 0 && ih < a.IH && iw >= 0 && iw < a.IW) x = in[((long long)ih * a.IW + iw) * a.Cin + (e & 255)];
+                    const int ih = ih0 + (e >> 24), iw = iw0 + ((e >> 16) & 255);
+                    if (ih >= 0 && ih < a.IH && iw >= 0 && iw < a.IW) x = in[((long long)ih * a.IW + iw) * a.Cin + (e & 0xFFFF)];
                 }
                 orow[k] = x;
             }
@@ -699,7 +699,7 @@ void im2col_pack(py::dict d) {
     a.wpack = lptr<float>(d, "wpack"); a.wpack_gs = lget<int64_t>(d, "wpack_gs", 0); a.Cout = lget<int>(d, "Cout", 0);
     const int G = d["G"].cast<int>();
     TORCH_CHECK(G >= 1 && a.eb >= 1 && a.Kpad % 4 == 0 && a.Kpad >= a.Kreal && (a.rng_step == nullptr || a.ticket != nullptr));
-    TORCH_CHECK(a.Cin < 256 && a.KW < 256 && a.KH < 256 && a.Kpad * 4 <= 48 * 1024, "im2col_pack: first-layer geometry out of range");
+    TORCH_CHECK(a.Cin < 65536 && a.KW < 256 && a.KH < 128 && a.Kpad * 4 <= 48 * 1024, "im2col_pack: first-layer geometry out of range");
     const long long pix = (long long)a.OH * a.OW;                          // 8 warps per block, one output pixel per warp pass
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(16, (pix + 7) / 8)), (unsigned)(a.eb + (a.wpack ? 1 : 0)), (unsigned)G);
     mb::im2col_pack_kernel<<<grid, 256, a.Kpad * sizeof(int), lstream()>>>(a);

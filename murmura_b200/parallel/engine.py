@@ -247,8 +247,29 @@ class B200Network:
         probe = model_factory()
         self.layout = StateLayout.from_model(probe, channels_last=bool(self.opt.channels_last))
         sketch_k = int(getattr(self.aggregator, "sketch_size", 0)) if self.family == "sketchguard" else 0
-        self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k,
-                                    backend="symm" if self.opt.transport == "nvls" else "ipc")
+        auto = self.opt.transport == "auto"
+        if auto:
+            # full-mesh FedAvg over several GPUs: every node computes the same sum → let the NVSwitch add the ranks' copies
+            # (each GPU ingests S·P instead of (N − V)·P bytes); everything else reads neighbour rows in-kernel over P2P
+            full = all(len(set(self.topology.neighbors[i]) - {i}) == self.N - 1 for i in range(self.N))
+            nvls = self.world > 1 and self.family == "fedavg" and full and self.mobility is None and not self.opt.fault_drop_edges
+            self.opt.transport = "nvls" if nvls else "p2p"
+        try:
+            self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k,
+                                        backend="symm" if self.opt.transport == "nvls" else "ipc")
+            ok = 1 if (self.opt.transport != "nvls" or self.arena.mc_base) else 0
+        except Exception:  # noqa: BLE001 - symmetric memory / multicast unavailable on this box
+            if not auto:
+                raise
+            ok = 0
+        if auto and self.opt.transport == "nvls":
+            if self.world > 1:                          # every rank must take the same path
+                t = torch.tensor([ok], device=self.device)
+                _dist().all_reduce(t, op=_dist().ReduceOp.MIN)
+                ok = int(t.item())
+            if not ok:
+                self.opt.transport = "p2p"
+                self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k, backend="ipc")
         S, L = self.placement.slots_per_rank, self.layout
         self.S = S
         self.live = self.arena.live
@@ -1177,64 +1198,13 @@ class B200Network:
 
     # ---- NCCL + stock-PyTorch baseline (b200.transport: nccl) -----------------------------------------
     def _aggregate_nccl(self, neighbors: List[List[int]]) -> None:
-        """The comparison baseline named in BASELINE.json: same placement and training, but the neighbour exchange is
-        ``torch.distributed`` NCCL send/recv along the edge list and the aggregation is the reference-parity aggregator
-        classes running stock PyTorch ops on the received state dicts (one aggregator instance per node, ``.item()``
-        syncs and all).  None of the fused kernels run on this path."""
-        L, pl = self.layout, self.placement
-        if not hasattr(self, "_nccl_aggs"):
-            self._nccl_aggs = {vn.gid: copy_aggregator(self.aggregator) for vn in self.nodes}
-        # 1. published copies (attack applied with torch ops)
-        pub_rows: Dict[int, torch.Tensor] = {}
-        pub_ints: Dict[int, torch.Tensor] = {}
-        for vn in self.nodes:
-            row = self.live[vn.slot].clone()
-            ints = self.ints[vn.slot].clone()
-            if vn.byzantine and self.attack is not None:
-                state = self.attack.apply_attack(node_id=vn.gid, model_state=dict(L.row_views(row, ints)), round_num=self.round_idx)
-                fresh = torch.zeros_like(row)
-                for k, v in L.row_views(fresh, None).items():
-                    v.copy_(state[k])
-                row = fresh
-            pub_rows[vn.gid], pub_ints[vn.gid] = row, ints
-        # 2. exchange along directed edges that cross ranks
-        recv_rows: Dict[Tuple[int, int], torch.Tensor] = {}
-        ops = []
-        dist = _dist() if self.world > 1 else None
-        order = [(j, i) for i in range(self.N) for j in neighbors[i] if pl.rank_of[i] != pl.rank_of[j]]   # (src, dst), same on all ranks
-        for src, dst in order:
-            rs, rd = int(pl.rank_of[src]), int(pl.rank_of[dst])
-            if rs == self.rank:
-                payload = torch.cat([pub_rows[src][: L.Pf_pad], pub_ints[src].float()])
-                ops.append(dist.P2POp(dist.isend, payload, rd))
-            elif rd == self.rank:
-                buf = torch.empty(L.Pf_pad + self.ints.shape[1], device=self.device)
-                recv_rows[(src, dst)] = buf
-                ops.append(dist.P2POp(dist.irecv, buf, rs))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        # 3. per-node aggregation with the stock classes on GPU tensors
-        results = []
-        for vn in self.nodes:
-            own = {k: v.clone() for k, v in L.row_views(self.live[vn.slot], self.ints[vn.slot]).items()}
-            nbrs = {}
-            for j in neighbors[vn.gid]:
-                if pl.rank_of[j] == self.rank:
-                    row, ints = pub_rows[j], pub_ints[j]
-                else:
-                    buf = recv_rows[(j, vn.gid)]
-                    row = torch.zeros(L.stride, device=self.device); row[: L.Pf_pad] = buf[: L.Pf_pad]
-                    ints = buf[L.Pf_pad:].round().long()
-                nbrs[j] = dict(L.row_views(row, ints if L.Pi else None))
-            loader = [(self._inputs(vn, vn.X[: max(vn.eb, 100)]), vn.y[: max(vn.eb, 100)])]
-            results.append(self._nccl_aggs[vn.gid].aggregate(node_id=vn.gid, own_state=own, neighbor_states=nbrs,
-                                                             round_num=self.round_idx, train_loader=loader,
-                                                             model_template=vn.model, device=self.device))
-        for vn, st in zip(self.nodes, results):
-            views = L.row_views(self.live[vn.slot], self.ints[vn.slot])
-            for k, v in st.items():
-                views[k].copy_(v.to(views[k].dtype))
+        """The comparison baseline named in BASELINE.json (``parallel/nccl_baseline.py``): same placement and training, flat-row
+        exchange over NCCL (one ``all_reduce`` on a full mesh, ``batch_isend_irecv`` along the edge list otherwise) and
+        vectorised stock-PyTorch aggregation.  None of the fused exchange / aggregation kernels run on this path."""
+        if not hasattr(self, "_nccl"):
+            from murmura_b200.parallel.nccl_baseline import NcclBaseline
+            self._nccl = NcclBaseline(self)
+        self._nccl.aggregate(neighbors)
 
     def _aggregate(self, parity: int) -> None:
         neighbors, key = self._neighbors_for_round(self.round_idx)

@@ -20,7 +20,7 @@ def test_schema_defaults_and_rejects():
     assert c.experiment.seed == 42 and c.experiment.rounds == 20 and c.topology.seed == 12345
     assert c.training.batch_size == 64 and c.training.lr == 0.01 and c.backend == "simulation"
     assert c.distributed.round_duration_s == 60.0 and c.attack.enabled is False and c.mobility is None
-    assert c.b200.transport == "p2p"
+    assert c.b200.transport == "auto" and c.b200.fused_train == "auto"
     with pytest.raises(ValidationError):
         Config(**{**_base(), "bogus": 1})                                  # unknown top-level key
     ok = _base(); ok["topology"]["whatever"] = 3; Config(**ok)              # unknown sub-key ignored
