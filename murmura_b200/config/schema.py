@@ -108,7 +108,9 @@ class B200Config(BaseModel):
     sketch_dtype: Literal["fp32", "fp8"] = Field(
         default="fp32", description="published Count-Sketch precision (fp8 = e4m3 + ue8m0 per 32)")
     krum_gram: Literal["auto", "tcgen05", "fp32"] = Field(
-        default="auto", description="pairwise-distance path: tcgen05 TF32 Gram or exact fp32 differences")
+        default="auto", description="Krum distances: fp32 = exact Σ(a−b)² (the reference's definition; auto picks it); tcgen05 = TF32 Gram "
+        "on tensor cores with an exact recomputation of every pair whose distance is below krum_refine_tau·(‖a‖²+‖b‖²)")
+    krum_refine_tau: float = Field(default=1e-2, description="cancellation guard of the tcgen05 Gram path (relative to ‖a‖²+‖b‖²)")
     channels_last: bool = Field(default=True, description="store 4-D weights / image shards NHWC (tensor-core conv path); "
                                 "aggregation is element-wise so the physical order is irrelevant to it")
     split_backward: Union[bool, Literal["auto"]] = Field(

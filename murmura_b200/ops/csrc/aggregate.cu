@@ -461,6 +461,61 @@ __global__ void __launch_bounds__(kThreads) pairwise_kernel(PairArgs a) {
     }
 }
 
+// ---- exact refinement of Gram-derived distances ---------------------------------------------------------------------------
+// D = G_aa + G_bb − 2·G_ab from a TF32 Gram carries an absolute error ∝ (‖a‖² + ‖b‖²); once honest models have converged the
+// true ‖a − b‖² is far below it (cancellation).  Every pair with D < τ·(‖a‖² + ‖b‖²) is therefore recomputed exactly
+// (Σ (a_k − b_k)² in fp32, the reference's definition: aggregation/base.py:118-135) — the fp32 fallback of SURVEY §7.3-2.
+// Pass 1: (pair, chunk) CTAs of flagged pairs stream both rows and add their partial sums into `scratch`; pass 2 substitutes.
+__device__ __forceinline__ void unrank_pair(int p, int& i, int& j) {
+    i = 0; int rem = p;
+    while (rem >= kPairM - 1 - i) { rem -= kPairM - 1 - i; ++i; }
+    j = i + 1 + rem;
+}
+
+__global__ void __launch_bounds__(kThreads) krum_refine_kernel(PairArgs a, const float* __restrict__ norms, float tau,
+                                                               float* __restrict__ scratch, int chunks) {
+    __shared__ float red[32];
+    const int v = blockIdx.y;
+    const int p = blockIdx.x / chunks, chunk = blockIdx.x - p * chunks;
+    int i, j; unrank_pair(p, i, j);
+    const int e0 = a.et.row_ptr[v];
+    const int m = min(a.et.row_ptr[v + 1] - e0, kPairM);
+    if (j >= m) return;
+    const float d = a.D[((size_t)v * kPairM + i) * kPairM + j];
+    if (!(d < tau * (norms[v * kPairM + i] + norms[v * kPairM + j]))) return;
+    const float* xi = (i == 0) ? a.live + (size_t)v * a.pv.stride : edge_src(a.pv, a.et, e0 + i);
+    const float* xj = edge_src(a.pv, a.et, e0 + j);
+    const int n4 = a.len >> 2;
+    const int per = (n4 + chunks - 1) / chunks;
+    const int lo = chunk * per, hi = min(n4, lo + per);
+    float s = 0.f;
+    for (int q = lo + threadIdx.x; q < hi; q += blockDim.x) {
+        const float4 x = ld_stream(reinterpret_cast<const float4*>(xi) + q), y = ld_stream(reinterpret_cast<const float4*>(xj) + q);
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(&scratch[((size_t)v * kPairM + i) * kPairM + j], s);
+}
+
+__global__ void krum_refine_apply_kernel(EdgeTable et, float* __restrict__ D, const float* __restrict__ norms, const float* __restrict__ scratch,
+                                         float tau, float* __restrict__ nref) {
+    const int v = blockIdx.x;
+    const int m = min(et.row_ptr[v + 1] - et.row_ptr[v], kPairM);
+    int cnt = 0;
+    for (int p = threadIdx.x; p < kPairM * (kPairM - 1) / 2; p += blockDim.x) {
+        int i, j; unrank_pair(p, i, j);
+        if (j >= m) continue;
+        float* dij = D + ((size_t)v * kPairM + i) * kPairM + j;
+        if (*dij < tau * (norms[v * kPairM + i] + norms[v * kPairM + j])) {
+            const float e = scratch[((size_t)v * kPairM + i) * kPairM + j];
+            *dij = e; D[((size_t)v * kPairM + j) * kPairM + i] = e;
+            ++cnt;
+        }
+    }
+    if (nref && cnt) atomicAdd(nref + v, (float)cnt);
+}
+
 // =============================================================================================
 // Count-Sketch: s[h(k)] += σ(k)·θ[k]; table packed as uint16 = bucket | (sign<0)<<15
 // =============================================================================================
@@ -686,16 +741,22 @@ __global__ void krum_select_kernel(FilterCommon c, int V, const float* D /*[V][3
     const int m = e1 - e0;
     for (int e = e0; e < e1; ++e) { c.w[e] = 0.f; c.w_tail[e] = 0.f; }
     int win = 0;
-    bool all_alive = true;
-    for (int e = e0 + 1; e < e1; ++e) all_alive = all_alive && edge_alive(c, e);
-    if (all_alive && m <= kPairM && (float)num_compromised < (float)(m - 2) * 0.5f) {
+    // Krum over the states that actually arrived (own + alive neighbours), like the reference's deadline-driven partial
+    // aggregation (distributed/node_process.py:241-244): a dropped / timed-out edge shrinks m instead of disabling the rule
+    int alive[kPairM]; int ma = 0;
+    if (m <= kPairM) {
+        alive[ma++] = 0;
+        for (int e = e0 + 1; e < e1; ++e) if (edge_alive(c, e)) alive[ma++] = e - e0;
+    }
+    if (ma >= 1 && (float)num_compromised < (float)(ma - 2) * 0.5f) {
         const float* Dv = D + (size_t)v * kPairM * kPairM;
-        const int keep = max(1, m - num_compromised - 2);
+        const int keep = max(1, ma - num_compromised - 2);
         float best = INFINITY;
-        for (int i = 0; i < m; ++i) {
+        for (int a = 0; a < ma; ++a) {
+            const int i = alive[a];
             float row[kPairM]; int n = 0;
-            for (int j = 0; j < m; ++j) if (j != i) {          // insertion sort of the m-1 distances
-                float d = sqrtf(fmaxf(Dv[i * kPairM + j], 0.f));
+            for (int b = 0; b < ma; ++b) if (b != a) {         // insertion sort of the distances to the other arrived states
+                float d = sqrtf(fmaxf(Dv[i * kPairM + alive[b]], 0.f));
                 int p = n++;
                 while (p > 0 && row[p - 1] > d) { row[p] = row[p - 1]; --p; }
                 row[p] = d;
@@ -896,6 +957,28 @@ void pairwise_distances(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, i
     const size_t smem = (size_t)max_m * mb::kPairTile * sizeof(float);
     dim3 grid(grid_x_for((int)len, mb::kPairTile, (int)V), (unsigned)V);
     mb::pairwise_kernel<<<grid, mb::kThreads, smem, cur_stream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// D [V][32][32] (Gram-derived squared distances) → pairs below τ·(‖a‖²+‖b‖²) replaced by their exact fp32 value; `scratch` like D.
+void krum_refine(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
+                 Tensor src_slot, Tensor mask, int64_t len, Tensor D, Tensor norms, double tau, Tensor scratch, c10::optional<Tensor> nref) {
+    if (V == 0) return;
+    c10::cuda::CUDAGuard guard(live.device());
+    TORCH_CHECK(D.numel() == V * mb::kPairM * mb::kPairM && scratch.numel() == D.numel() && norms.numel() == V * mb::kPairM);
+    mb::PairArgs a;
+    a.live = live.data_ptr<float>();
+    a.pv = mb::PeerView{reinterpret_cast<const float* const*>(peer_pub_ptr), (size_t)parity_off, (size_t)stride};
+    a.et = make_et(row_ptr, src_rank, src_slot, mask);
+    a.len = (int)len; a.D = D.data_ptr<float>();
+    a.flags = nullptr; a.G = 1; a.epoch = 0; a.timeout = 0; a.timed_out = nullptr;
+    cudaMemsetAsync(scratch.data_ptr<float>(), 0, scratch.numel() * sizeof(float), cur_stream());
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, len / (64 * 1024)));
+    dim3 grid((unsigned)(mb::kPairM * (mb::kPairM - 1) / 2 * chunks), (unsigned)V);
+    mb::krum_refine_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a, norms.data_ptr<float>(), (float)tau, scratch.data_ptr<float>(), chunks);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    mb::krum_refine_apply_kernel<<<(unsigned)V, 128, 0, cur_stream()>>>(a.et, D.data_ptr<float>(), norms.data_ptr<float>(), scratch.data_ptr<float>(),
+                                                                       (float)tau, nref.has_value() ? nref->data_ptr<float>() : nullptr);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

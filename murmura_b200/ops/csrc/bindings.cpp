@@ -25,6 +25,8 @@ void edge_distances(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64
 void pairwise_distances(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
                         Tensor src_slot, Tensor mask, int64_t len, Tensor D, int64_t max_m, int64_t flags_ptr, int64_t G, int64_t epoch,
                         double timeout_ms, int64_t timed_out_ptr);
+void krum_refine(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr, Tensor src_rank,
+                 Tensor src_slot, Tensor mask, int64_t len, Tensor D, Tensor norms, double tau, Tensor scratch, c10::optional<Tensor> nref);
 void count_sketch(int64_t base_ptr, int64_t stride, Tensor slots, Tensor table, int64_t Pf, int64_t K, Tensor out);
 void sketch_quant_mxfp8(Tensor sk, int64_t q_ptr, int64_t sc_ptr, int64_t Kpad);
 void fedavg_weights(int64_t V, Tensor row_ptr, Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, Tensor w_tail, Tensor stats);
@@ -99,6 +101,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("nvls_fedavg", &nvls_fedavg);
     m.def("edge_distances", &edge_distances);
     m.def("pairwise_distances", &pairwise_distances);
+    m.def("krum_refine", &krum_refine, "exact fp32 recomputation of the cancellation-prone pairs of a Gram-derived distance table");
     m.def("count_sketch", &count_sketch);
     m.def("sketch_quant_mxfp8", &sketch_quant_mxfp8);
     m.def("fedavg_weights", &fedavg_weights);

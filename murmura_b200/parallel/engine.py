@@ -642,44 +642,49 @@ class B200Network:
         live = [vn for vn in self.nodes if not vn.byzantine and vn.nb > 0]
         if not live:
             return None
-        if len({vn.eb for vn in live}) != 1:
-            return None                                         # mixed effective batch sizes (a shard smaller than the batch)
         first = self.nodes[0]
         if first.X.dim() == 4 and not first.nhwc:
             return None
         shape = (first.X.shape[3], first.X.shape[1], first.X.shape[2]) if first.X.dim() == 4 else tuple(first.X.shape[1:])
-        steps = [0 if (vn.byzantine or vn.nb == 0) else epochs * vn.nb for vn in self.nodes]
-        tr = FusedTrainer(first.model, self.layout, self.live, self.ints if self.layout.Pi else None, [(vn.X, vn.y) for vn in self.nodes],
-                          steps, live[0].eb, shape, evidential=self.evidential, seed=int(self.cfg.experiment.seed),
-                          side_stream=bool(self.opt.fused_side_stream))
-        if not tr.supported:
-            if mode is True and self.is_primary:
-                print(f"[b200] fused_train unavailable for this model ({getattr(tr, 'unsupported_reason', 'unsupported family')}); "
-                      "using per-node autograd graphs")
-            return None
-        tr.lam_t = self.lam_t                                    # annealing coefficient is read on the device
-        return tr
+        trainers = []
+        # one program per effective batch size (a shard smaller than the batch trains with batch = shard size, reference
+        # core/network.py:280-287): the nodes of the other sizes simply have zero steps in it
+        for eb in sorted({vn.eb for vn in live}, reverse=True):
+            steps = [epochs * vn.nb if (not vn.byzantine and vn.nb > 0 and vn.eb == eb) else 0 for vn in self.nodes]
+            tr = FusedTrainer(first.model, self.layout, self.live, self.ints if self.layout.Pi else None, [(vn.X, vn.y) for vn in self.nodes],
+                              steps, eb, shape, evidential=self.evidential, seed=int(self.cfg.experiment.seed),
+                              side_stream=bool(self.opt.fused_side_stream))
+            if not tr.supported:
+                if mode is True and self.is_primary:
+                    print(f"[b200] fused_train unavailable for this model ({getattr(tr, 'unsupported_reason', 'unsupported family')}); "
+                          "using per-node autograd graphs")
+                return None
+            tr.lam_t = self.lam_t                                # annealing coefficient is read on the device
+            trainers.append(tr)
+        return trainers
 
     def _fused_training(self, epochs: int, lr: float) -> bool:
         cache = self.__dict__.setdefault("_fused_cache", {})
         if epochs not in cache:
             cache[epochs] = self._fused_setup(epochs)
-        tr = cache[epochs]
-        if tr is None:
+        trainers = cache[epochs]
+        if trainers is None:
             return False
         if self._host_shards:                                    # end-to-end mode: this round's inputs come from pinned host memory
             for i, vn in enumerate(self.nodes):
                 vn.X.copy_(self._host_shards[i][0], non_blocking=True)
                 vn.y.copy_(self._host_shards[i][1], non_blocking=True)
-        tr.loss_acc.zero_()
-        before = tr.be.launches
-        tr.run_round(epochs, lr)
-        if tr.be.launches > before:                              # the round was (re)captured: remember its launch count
-            tr.launches_in_graph = (tr.be.launches - before) * tr.max_steps // (tr.max_steps + 1) if tr.max_steps else 0
-        self.kernel_launches += getattr(tr, "launches_in_graph", 0)
-        for vn in self.nodes:
-            vn.loss_sum = tr.loss_acc[vn.slot]
-        self.fused = tr
+        for tr in trainers:
+            tr.loss_acc.zero_()
+            before = tr.be.launches
+            tr.run_round(epochs, lr)
+            if tr.be.launches > before:                          # the round was (re)captured: remember its launch count
+                tr.launches_in_graph = (tr.be.launches - before) * tr.max_steps // (tr.max_steps + 1) if tr.max_steps else 0
+            self.kernel_launches += getattr(tr, "launches_in_graph", 0)
+            for vn in self.nodes:
+                if tr.steps[vn.slot] > 0:
+                    vn.loss_sum = tr.loss_acc[vn.slot]
+        self.fused = trainers[0]
         return True
 
     # ---- K8b: all MLP nodes of this GPU in one batched step (opt-in: b200.batched_mlp_train) ------------------------------
@@ -921,8 +926,8 @@ class B200Network:
 
     def _gram_plan(self, et) -> Optional[Dict[str, Any]]:
         """Tile plan for the tcgen05 Gram: rows = live+published planes of every rank."""
-        if self.opt.krum_gram == "fp32":
-            return None
+        if self.opt.krum_gram != "tcgen05":
+            return None                                  # auto = exact fp32 differences (the reference's distances); the Gram is opt-in
         if "gram_plan" in et:
             return et["gram_plan"]
         S, G, L = self.S, self.world, self.layout
@@ -969,8 +974,16 @@ class B200Network:
                 _dist().all_reduce(Gm)
             diag = Gm.diagonal()
             idx = plan["idx"]
-            D = diag[idx].unsqueeze(2) + diag[idx].unsqueeze(1) - 2.0 * Gm[idx.unsqueeze(2), idx.unsqueeze(1)]
+            norms = diag[idx].contiguous()                # ‖θ‖² of every candidate of every local node, [V, 32]
+            D = norms.unsqueeze(2) + norms.unsqueeze(1) - 2.0 * Gm[idx.unsqueeze(2), idx.unsqueeze(1)]
             et["krum_D"].copy_(D.clamp_min_(0.0))
+            # TF32 Gram error ∝ ‖θ‖²: pairs whose distance drowns in it (converged honest models) are recomputed exactly
+            if "krum_scratch" not in et:
+                et["krum_scratch"] = torch.zeros_like(et["krum_D"]); et["krum_refined"] = torch.zeros(max(self.V, 1), device=self.device)
+            self.ext.krum_refine(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
+                                 et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], L.Pf_pad, et["krum_D"], norms,
+                                 float(self.opt.krum_refine_tau), et["krum_scratch"], et["krum_refined"])
+            self.kernel_launches += 2
         else:
             self.ext.pairwise_distances(self.live, self.arena.tbl_pub.data_ptr(), self.arena.parity_off(parity), L.stride, self.V,
                                         et["row_ptr"], et["src_rank"], et["src_slot"], et["mask"], L.Pf_pad, et["krum_D"],
@@ -1058,6 +1071,12 @@ class B200Network:
         xb.copy_(x.reshape(x.shape[0], -1)); yb.copy_(y)
         return xb, yb
 
+    def _arange(self, n: int) -> torch.Tensor:
+        t = self._row_cache.get(("arange", n))
+        if t is None:
+            t = self._row_cache[("arange", n)] = torch.arange(n, device=self.device)
+        return t
+
     def _evaluator(self, vn: VirtualNode, rows: int, kind: str) -> ForeignEval:
         key = (vn.slot, rows, kind)
         ev = self._evaluators.get(key)
@@ -1071,6 +1090,64 @@ class B200Network:
         if row is None:
             row = self._row_cache[key] = self.arena.peer_row(rank, parity, slot)
         return row
+
+    # ---- fused scoring of foreign weights: ONE grouped forward program for every (destination, candidate) pair -------------------
+    def _score_program(self, rows: int, capacity: int):
+        """``FusedForward`` over ``capacity`` (destination, candidate) groups of ``rows`` samples each, or ``None`` when the model
+        family is not covered by the fused tape (then the per-candidate graph replays of :class:`ForeignEval` are used)."""
+        from murmura_b200.parallel.fused_trainer import FusedForward
+        if not self.opt.fused_train or not self.nodes or self.opt.compute_dtype == "bf16":
+            return None
+        key = ("score", rows)
+        st = self._evaluators.get(key)
+        if st is not None and st["cap"] >= capacity:
+            return st
+        first = self.nodes[0]
+        if first.X.dim() == 4 and not first.nhwc:
+            return None
+        shape = (first.X.shape[3], first.X.shape[1], first.X.shape[2]) if first.X.dim() == 4 else tuple(first.X.shape[1:])
+        cap = max(capacity, 16)
+        fe = FusedForward(first.model, self.layout, self.live, rows, shape, cap, evidential=self.evidential)
+        if not fe.supported:
+            self._evaluators[key] = {"cap": 1 << 30, "fe": None}
+            return self._evaluators[key]
+        dev = self.device
+        st = {"cap": cap, "fe": fe, "row_tab": torch.zeros(cap, dtype=torch.int64, device=dev),
+              "perm": torch.zeros(self.V, rows, dtype=torch.int64, device=dev),
+              "x_tab": torch.tensor([vn.X.data_ptr() for vn in self.nodes], dtype=torch.int64, device=dev),
+              "y_tab": torch.tensor([vn.y.data_ptr() for vn in self.nodes], dtype=torch.int64, device=dev),
+              "stats": torch.zeros(cap, _STAT_COLS, device=dev)}
+        fe.row_tab = st["row_tab"]
+        self._evaluators[key] = st
+        return st
+
+    def _fused_scores(self, jobs: List[Tuple[int, int, int]], samples: Dict[int, torch.Tensor], rows: int, kind: str, stats: torch.Tensor) -> bool:
+        """``jobs`` = (stats row, destination vi, candidate row address); ``samples[vi]`` = sample indices of the destination
+        (≤ ``rows``).  Everything is enqueued on the current stream; no host synchronisation."""
+        if not jobs:
+            return True
+        st = self._score_program(rows, len(jobs))
+        if st is None or st["fe"] is None:
+            return False
+        fe, G = st["fe"], len(jobs)
+        valid = []
+        for vi, idx in samples.items():
+            k = int(idx.numel())
+            st["perm"][vi, :k] = idx
+            if k < rows:
+                st["perm"][vi, k:] = idx[-1]
+        for _, vi, _ in jobs:
+            valid.append(int(samples[vi].numel()))
+        fe.gmap[:G] = torch.tensor([vi for _, vi, _ in jobs], dtype=torch.int32, device=self.device)
+        st["row_tab"][:G] = torch.tensor([a for _, _, a in jobs], dtype=torch.int64, device=self.device)
+        fe.load(G, st["x_tab"], st["y_tab"], st["perm"], 0)
+        fe.forward(G)
+        tmp = st["stats"][:G]
+        tmp.zero_()
+        fe.metrics(G, fe.eval_descriptors(valid), tmp, dirichlet=(kind == "dirichlet"))
+        stats.index_copy_(0, torch.tensor([j[0] for j in jobs], device=self.device), tmp)
+        self.kernel_launches += len(fe.ops) + 2
+        return True
 
     # ---- UBAR --------------------------------------------------------------------------------
     def _ubar_prepare(self, et, parity: int) -> None:
@@ -1094,10 +1171,29 @@ class B200Network:
             self._ubar_prepare(et, parity)
         tp = self._sync_args()[4]
         cand, rank_t, loss, own_loss = et["aux"], et["aux2"], et["aux3"], et["n2"]
-        self._cand_event.synchronize()                               # tiny D2H issued earlier: which candidates to evaluate
-        cand_host = self._cand_pinned[: cand.numel()]
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
+        # fused path: score EVERY neighbour in one grouped forward program and let ubar_stage2 mask with the device-side
+        # shortlist — no host round-trip between stage 1 and stage 2 (reference aggregation/ubar.py:152-202)
+        jobs, samples = [], {}
+        for vi, vn in enumerate(self.nodes):
+            if rows[vi + 1] - rows[vi] <= 1 or vn.n == 0:
+                continue
+            samples[vi] = torch.randperm(vn.n, device=self.device)[: vn.eb]
+            jobs.append((rows[vi], vi, self._row_ptr(self.rank, None, vn.slot)))
+            jobs += [(e, vi, self._row_ptr(rk[e], parity, sl[e])) for e in range(rows[vi] + 1, rows[vi + 1])]
+        eb_max = max([vn.eb for vn in self.nodes] or [1])
+        if self._fused_scores(jobs, samples, eb_max, "ce", stats):
+            mean_loss = stats[:, 0] / stats[:, 2].clamp_min(1.0)
+            loss.copy_(mean_loss[: loss.numel()])
+            if self.V:
+                own_loss[: self.V] = mean_loss[torch.tensor(rows[: self.V], device=self.device)]
+            self.ext.ubar_stage2(*self._et_args(et), cand, rank_t, loss, own_loss, a.alpha, True)
+            self.kernel_launches += 1
+            self._log_stats(et)
+            return self._gather(et, parity, renorm=False, sync=False)
+        self._cand_event.synchronize()                               # tiny D2H issued earlier: which candidates to evaluate
+        cand_host = self._cand_pinned[: cand.numel()]
         if self._mlp_plan is not None:
             jobs, inputs = [], {}
             for vi, vn in enumerate(self.nodes):
@@ -1139,7 +1235,21 @@ class B200Network:
         vac, acc, trust = et["aux"], et["aux2"], et["aux3"]
         rows, rk, sl = et["host_rows"], et["host_rank"], et["host_slot"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
-        if self._mlp_plan is not None:
+        jobs, samples, take_max = [], {}, 1
+        for vi, vn in enumerate(self.nodes):
+            if vn.n == 0:
+                continue
+            nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
+            take_n = min(vn.n, nbatch * vn.eb)
+            if vn.n > vn.eb:
+                take_n = (take_n // vn.eb) * vn.eb               # the reference iterates a drop_last loader: whole batches only
+            samples[vi] = torch.randperm(vn.n, device=self.device)[:take_n]
+            take_max = max(take_max, take_n)
+            jobs += [(e, vi, self._row_ptr(rk[e], parity, sl[e])) for e in range(rows[vi] + 1, rows[vi + 1])]
+        fused_done = self._fused_scores(jobs, samples, take_max, "dirichlet", stats)
+        if fused_done:
+            pass
+        elif self._mlp_plan is not None:
             jobs, inputs = [], {}
             for vi, vn in enumerate(self.nodes):
                 if vn.n == 0:
@@ -1151,7 +1261,7 @@ class B200Network:
             self._grouped_mlp_scores(jobs, inputs, "dirichlet", stats)
         self._fork()
         for vi, vn in enumerate(self.nodes):
-            if vn.n == 0 or self._mlp_plan is not None:
+            if vn.n == 0 or self._mlp_plan is not None or fused_done:
                 continue
             with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 nbatch = max(1, math.ceil(a.max_eval_samples / max(vn.eb, 1)))
@@ -1431,7 +1541,17 @@ class B200Network:
         received = torch.zeros(V, N, dtype=torch.uint8, device=self.device)
         rows, rk, sl, gids = et["host_rows"], et["host_rank"], et["host_slot"], et["host_gid"]
         stats = torch.zeros(max(len(rk), 1), _STAT_COLS, device=self.device)
-        if self._mlp_plan is not None:
+        jobs, samples = [], {}
+        for vi, vn in enumerate(self.nodes):
+            if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1:
+                continue
+            samples[vi] = self._arange(vn.n)                         # the whole local test set (= training shard), reference dmtt/node_process.py:309-363
+            jobs += [(e, vi, self._row_ptr(rk[e], parity, sl[e])) for e in range(rows[vi] + 1, rows[vi + 1])]
+        n_max = max([vn.n for vn in self.nodes] or [1])
+        fused_done = self._fused_scores(jobs, samples, n_max, "dirichlet" if self.evidential else "ce", stats)
+        if fused_done:
+            pass
+        elif self._mlp_plan is not None:
             jobs, inputs = [], {}
             for vi, vn in enumerate(self.nodes):
                 if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1:
@@ -1441,7 +1561,7 @@ class B200Network:
             self._grouped_mlp_scores(jobs, inputs, "dirichlet" if self.evidential else "ce", stats)
         self._fork()
         for vi, vn in enumerate(self.nodes):
-            if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1 or self._mlp_plan is not None:
+            if vn.n == 0 or rows[vi + 1] - rows[vi] <= 1 or self._mlp_plan is not None or fused_done:
                 continue
             with torch.cuda.stream(self.streams[self.stream_of[vi]]):
                 ev = self._evaluator(vn, vn.n, "dirichlet" if self.evidential else "ce")

@@ -384,3 +384,42 @@ def test_training_with_split_backward_modes(split):
         assert used == (split is True)                     # 4 nodes on one GPU: "auto" keeps the single-stream backward
     finally:
         net.close()
+
+
+@pytest.mark.parametrize("gram", ["fp32", "tcgen05"])
+def test_krum_on_converged_models_matches_fp64_oracle(gram):
+    """Honest models that have (almost) converged + two far outliers: the distance table and the Krum winner of every node must
+    match an fp64 oracle.  The TF32 Gram alone cannot resolve ‖a−b‖² ≪ ‖a‖² (cancellation): the tcgen05 path recomputes those
+    pairs exactly (``krum_refine_kernel``), ``auto`` / ``fp32`` use exact differences throughout."""
+    n = 8
+    cfg = _cfg("krum", params={"num_compromised": 1}, n=n, topo={"type": "fully", "num_nodes": n},
+               model={"factory": "models.mlp", "params": {"hidden_dims": [256]}}, b200={"krum_gram": gram})
+    net, _, _ = _build(cfg)
+    try:
+        L = net.layout
+        g = torch.Generator(device="cuda").manual_seed(5)
+        base = torch.randn(L.Pf, device=net.device, generator=g)
+        for vn in net.nodes:
+            noise = 1e-3 if vn.gid not in (2, 5) else 0.5
+            net.live[vn.slot, : L.Pf] = base + noise * torch.randn(L.Pf, device=net.device, generator=g)
+        X = net.live[: net.V, : L.Pf].double().cpu()
+        net._aggregate(parity=0)
+        torch.cuda.synchronize()
+        et = net._last_et
+        rows, gids = et["host_rows"], et["host_gid"]
+        D = et["krum_D"].cpu().double()
+        win = et["krum_win"].cpu()
+        for vi, vn in enumerate(net.nodes):
+            ids = gids[rows[vi]:rows[vi + 1]]
+            A = X[[net.placement.slot_of[j] for j in ids]]
+            D64 = torch.cdist(A, A) ** 2
+            m = len(ids)
+            got = D[vi, :m, :m]
+            assert torch.allclose(got, D64, rtol=2e-3, atol=1e-6), (gram, vi, (got - D64).abs().max())
+            k = max(1, m - 1 - 2)
+            score = (D64 + torch.diag(torch.full((m,), float("inf")))).sqrt().sort(dim=1).values[:, :k].sum(1)
+            assert int(win[vi]) == int(score.argmin()), (gram, vi)
+        if gram == "tcgen05":
+            assert float(et["krum_refined"].sum()) > 0          # the near-identical honest pairs went through the exact recomputation
+    finally:
+        net.close()
