@@ -128,6 +128,8 @@ class B200Config(BaseModel):
         default="auto", description="train all nodes of a GPU with the fused tcgen05 program (parallel/fused_trainer.py: grouped implicit-GEMM "
                                     "conv / linear kernels with the SGD step in the wgrad epilogue, one CUDA graph per round); auto = whenever the "
                                     "model family, loss and layout are supported, otherwise the per-node autograd graphs")
+    fused_eval_rows: int = Field(default=256, description="fused evaluation: samples per node and launch (nodes are sorted by shard size, so a "
+                                 "chunk only runs the nodes that still have samples: no padding to the largest shard)")
     fused_side_stream: bool = Field(default=True, description="fused_train: weight-gradient launches on a parallel graph branch")
     batched_mlp_train: bool = Field(default=False, description="train all MLP-family nodes of a GPU in one batched step (strided-batched GEMMs "
                                     "over arena-row views, masked per-node BatchNorm/SGD); opt-in, falls back to per-node graphs")
@@ -135,7 +137,8 @@ class B200Config(BaseModel):
                               "grouped tcgen05 forward (TF32) instead of per-candidate graph replays (fp32)")
     streams: int = Field(default=0, description="concurrent CUDA streams for virtual-node training (0 = auto: min(16, nodes on this GPU))")
     eval_batch: int = Field(default=1024, description="evaluation micro-batch (results are batch-size independent)")
-    flag_timeout_ms: float = Field(default=5000.0, description="device-side wait budget for a peer's publish flag")
+    flag_timeout_ms: float = Field(default=60000.0, description="device-side wait budget for a peer's publish flag; a rank that stays silent "
+                                   "longer is treated as missing for the round (and reported): the reference's deadline-driven partial aggregation")
     fault_drop_edges: Dict[int, list] = Field(
         default_factory=dict, description="fault injection: {round: [[src, dst], ...]} edges to drop")
     checkpoint_every: int = Field(default=0, description="save arena checkpoint every k rounds (0 = off)")

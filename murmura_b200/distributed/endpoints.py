@@ -13,14 +13,20 @@ class Endpoints:
     def _ipc(self, leaf: str) -> str:
         return f"ipc://{self.cfg.ipc_dir}/{self.run_id}/{leaf}"
 
+    @staticmethod
+    def _bind_host(own: str) -> str:
+        """PULL sockets bind to the node's own configured host, not to every interface (payloads are pickles, as in the reference);
+        ``MURMURA_BIND_HOST=0.0.0.0`` restores the reference's bind-all behaviour on a trusted network."""
+        return os.environ.get("MURMURA_BIND_HOST") or own
+
     def monitor_pull_bind(self) -> str:
-        return self._ipc("monitor_pull") if self.cfg.transport == "ipc" else f"tcp://0.0.0.0:{self.cfg.coordinator_pull_port}"
+        return self._ipc("monitor_pull") if self.cfg.transport == "ipc" else f"tcp://{self._bind_host(self.cfg.host)}:{self.cfg.coordinator_pull_port}"
 
     def monitor_pull_connect(self) -> str:
         return self._ipc("monitor_pull") if self.cfg.transport == "ipc" else f"tcp://{self.cfg.host}:{self.cfg.coordinator_pull_port}"
 
     def node_pull_bind(self, node_id: int) -> str:
-        return self._ipc(f"node_{node_id}") if self.cfg.transport == "ipc" else f"tcp://0.0.0.0:{self.cfg.base_port + node_id}"
+        return self._ipc(f"node_{node_id}") if self.cfg.transport == "ipc" else f"tcp://{self._bind_host((self.cfg.node_hosts or {}).get(node_id, self.cfg.host))}:{self.cfg.base_port + node_id}"
 
     def node_pull_connect(self, node_id: int) -> str:
         if self.cfg.transport == "ipc":

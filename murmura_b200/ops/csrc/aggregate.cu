@@ -834,7 +834,12 @@ Sync make_sync(int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, i
     Sync s;
     s.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
     s.G = (int)G; s.epoch = (uint32_t)epoch;
-    s.timeout = (long long)(timeout_ms * 1.9e6);       // ~1.9 GHz SM clock → cycles
+    static int khz = 0;                                  // clock64() ticks at the SM clock: cycles per millisecond = kHz
+    if (khz == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1900000;
+    }
+    s.timeout = (long long)(timeout_ms * (double)khz);
     s.timed_out = reinterpret_cast<uint32_t*>(timed_out_ptr);
     return s;
 }

@@ -12,10 +12,12 @@ namespace mb {
 constexpr int kMaxRanks = 16;
 
 // ---- memory access -------------------------------------------------------------------------
-// Streaming 128-bit load that does not pollute L1 (neighbour tiles are read exactly once).
+// Streaming 128-bit load that does not pollute L1 (neighbour tiles are read exactly once).  Coherent on purpose (no `.nc`): peer
+// rows are written while a consumer may already be resident and spinning on the epoch flag, and the acquire on that flag only
+// orders the coherent path.
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }

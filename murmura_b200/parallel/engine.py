@@ -778,6 +778,10 @@ class B200Network:
     def _sync_args(self) -> Tuple[int, int, int, float, int]:
         if self.world == 1:
             return 0, 1, 0, 0.0, 0
+        if getattr(self, "_liveness_frozen", False):
+            # liveness was decided ONCE for this round by the wait_epoch launch: later kernels do not spin, they only apply the
+            # frozen timed-out mask (no torn rows when a flag lands near the deadline)
+            return 0, self.world, 0, 0.0, self.arena.timed_out_ptr()
         return self.arena.flags_ptr(), self.world, self.epoch, float(self.opt.flag_timeout_ms), self.arena.timed_out_ptr()
 
     def _publish(self, parity: int) -> None:
@@ -917,6 +921,7 @@ class B200Network:
                          self.atk_scale, self.atk_noise, self.node_gid, 0, 0, self.arena.tbl_flags.data_ptr(), self.world,
                          self.rank, self.epoch, self.ticket)
         self.kernel_launches += 1
+        self._freeze_liveness()                           # the consumers of the auxiliary data wait for THIS epoch
 
     # ---- Krum --------------------------------------------------------------------------------
     def _krum_tables(self, et) -> None:
@@ -997,8 +1002,21 @@ class B200Network:
     def _host_wait_epoch(self) -> None:
         """Block the *stream* (not the host) until all ranks published (1-warp spin kernel)."""
         fp, G, ep, to, tp = self._sync_args()
-        self.ext.wait_epoch(self.live, fp, G, ep, to, tp)
-        self.kernel_launches += 1
+        if fp:
+            self.ext.wait_epoch(self.live, fp, G, ep, to, tp)
+            self.kernel_launches += 1
+
+    def _freeze_liveness(self) -> None:
+        """One wait on the epoch flags decides which peers arrived; every later kernel of the round consumes that mask."""
+        if self.world == 1:
+            return
+        self._liveness_frozen = False
+        self._host_wait_epoch()
+        self._liveness_frozen = True
+        if not hasattr(self, "_timeout_acc"):
+            self._timeout_acc = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._timeout_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._timeout_acc |= self.arena.timed_out
 
     # ---- forward evaluation of foreign weights (UBAR stage 2, EvidentialTrust, DMTT scoring) ----------------
     def _forward_with(self, vn: VirtualNode, state: Optional[Dict[str, torch.Tensor]], xb: torch.Tensor) -> torch.Tensor:
@@ -1323,7 +1341,9 @@ class B200Network:
                 et = self._edge_table(neighbors, key)
                 if self.world > 1:
                     self.arena.timed_out.zero_()
+                    self._liveness_frozen = False
                 self._publish(parity)
+                self._freeze_liveness()
                 self._dmtt_score_and_update(et, parity)
             return self._aggregate_nccl(neighbors)
         et = self._edge_table(neighbors, key)
@@ -1331,7 +1351,9 @@ class B200Network:
             self._apply_fault_mask(et, self.round_idx)
         if self.world > 1:
             self.arena.timed_out.zero_()
+            self._liveness_frozen = False
         self._publish(parity)
+        self._freeze_liveness()
         if self.family == "ubar":
             self._ubar_prepare(et, parity)
         if self.dmtt_on:
@@ -1384,7 +1406,7 @@ class B200Network:
             return None
         shape = (first.X.shape[3], first.X.shape[1], first.X.shape[2]) if first.X.dim() == 4 else tuple(first.X.shape[1:])
         n_max = max(vn.n for vn in self.nodes)
-        EB = min(max(1, self.opt.eval_batch), (n_max + 31) // 32 * 32)
+        EB = min(max(32, int(self.opt.fused_eval_rows)), (n_max + 31) // 32 * 32)
         fe = FusedForward(first.model, self.layout, self.live, EB, shape, self.V, evidential=self.evidential)
         if not fe.supported or (self.evidential and not fe.evidential_head):
             return None
@@ -1464,7 +1486,15 @@ class B200Network:
         else:
             full = local
         self.metrics_host[: full.shape[0]].copy_(full, non_blocking=True)
+        if self.world > 1 and hasattr(self, "_timeout_acc"):
+            self._timeout_host.copy_(self._timeout_acc, non_blocking=True)
+            self._timeout_acc.zero_()
         torch.cuda.current_stream().synchronize()          # the one host sync per evaluated round
+        if self.world > 1 and hasattr(self, "_timeout_host") and int(self._timeout_host[0]):
+            late = [r for r in range(self.world) if int(self._timeout_host[0]) >> r & 1]
+            self.timeout_events = getattr(self, "timeout_events", []) + [(self.round_idx + 1, late)]
+            print(f"[b200 rank {self.rank}] round {self.round_idx + 1}: rank(s) {late} did not publish within "
+                  f"{self.opt.flag_timeout_ms:.0f} ms; their nodes were aggregated as missing neighbours")
         host = self.metrics_host.numpy()
         per_node = []
         for gid in range(self.N):

@@ -144,7 +144,7 @@ def test_dmtt_state_math():
     big = DMTTNodeState(0, DMTTConfig()); big.update_trust(7, 1, 0); assert big._alpha[7] == pytest.approx(1.9)
 
 
-def test_messaging_roundtrip():
+def test_messaging_roundtrip(monkeypatch):
     from murmura_b200.distributed.messaging import MsgType, decode, decode_full, encode, pack_obj, pack_state, unpack_obj, unpack_state
     import struct
     frames = encode(MsgType.TOPO_CLAIM, 5, b"xyz", round_idx=9)
@@ -156,7 +156,11 @@ def test_messaging_roundtrip():
     from murmura_b200.distributed.endpoints import Endpoints
     from murmura_b200.config.schema import DistributedConfig
     ep = Endpoints(DistributedConfig(transport="tcp", node_hosts={2: "10.0.0.2"}), 3, "r1")
-    assert ep.node_pull_connect(2) == "tcp://10.0.0.2:5552" and ep.node_pull_bind(1) == "tcp://0.0.0.0:5551"
+    assert ep.node_pull_connect(2) == "tcp://10.0.0.2:5552" and ep.node_pull_bind(1) == "tcp://127.0.0.1:5551"
+    assert len(frames[0]) == 5 and struct.unpack("!Bi", frames[0]) == (2, 5)          # frame 0 stays the reference's 5-byte header
+    assert decode_full([struct.pack("!Bii", 1, 4, 7), b"q"]) == (MsgType.METRICS, 4, 7, b"q")   # round-1 header still accepted
+    monkeypatch.setenv("MURMURA_BIND_HOST", "0.0.0.0")
+    assert Endpoints(DistributedConfig(transport="tcp"), 3, "r1").node_pull_bind(1) == "tcp://0.0.0.0:5551"
     assert Endpoints(DistributedConfig(), 3, "r1").monitor_pull_bind() == "ipc:///tmp/murmura/r1/monitor_pull"
 
 
