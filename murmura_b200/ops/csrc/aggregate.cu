@@ -97,6 +97,62 @@ __global__ void __launch_bounds__(kThreads) publish_kernel(PublishArgs a) {
 }
 
 // =============================================================================================
+// publish + per-rank column sum (full-mesh FedAvg): the same pass that writes the published rows also writes
+// rsum = Σ_v published_v, so the aggregate needs ONE row per rank from the fabric instead of every node's row.
+// One thread owns a float4 column of all V local rows (V is small); bytes = publish bytes + one extra row written.
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads) publish_sum_kernel(PublishArgs a, float* __restrict__ rsum, int V) {
+    const int n4 = a.Pf_pad >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        int v = 0;
+        auto one = [&](float4 x, int vv) {
+            const float sc = a.scale[vv], sd = a.noise_std[vv];
+            if (sc != 1.f) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
+            if (sd != 0.f) {
+                const float4 z = philox_normal4(a.seed, a.round * 1000003ull + (uint64_t)a.node_gid[vv], (uint64_t)i);
+                const int base = i << 2;
+                if (base + 0 < a.Pf) x.x = fmaf(sd, z.x, x.x);
+                if (base + 1 < a.Pf) x.y = fmaf(sd, z.y, x.y);
+                if (base + 2 < a.Pf) x.z = fmaf(sd, z.z, x.z);
+                if (base + 3 < a.Pf) x.w = fmaf(sd, z.w, x.w);
+            }
+            st_stream(reinterpret_cast<float4*>(a.pub + (size_t)vv * a.stride) + i, x);
+            sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+        };
+        for (; v + 4 <= V; v += 4) {                       // 4 independent 128-bit loads in flight
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = ld_stream(reinterpret_cast<const float4*>(a.live + (size_t)(v + u) * a.stride) + i);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) one(x[u], v + u);
+        }
+        for (; v < V; ++v) one(ld_stream(reinterpret_cast<const float4*>(a.live + (size_t)v * a.stride) + i), v);
+        st_stream(reinterpret_cast<float4*>(rsum) + i, sum);
+    }
+    if (blockIdx.x == 0 && a.n_int > 0) {
+        for (int v = 0; v < V; ++v) {
+            float* lt = a.live + (size_t)v * a.stride + a.Pf_pad;
+            float* pt = a.pub + (size_t)v * a.stride + a.Pf_pad;
+            for (int k = threadIdx.x; k < a.n_int; k += blockDim.x) {
+                const float f = (float)a.ints[(size_t)v * a.n_int + k];
+                lt[k] = f; pt[k] = f;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            *a.ticket = 0;
+            if (a.peer_flags != nullptr)
+                for (int g = 0; g < a.G; ++g) st_release_sys(a.peer_flags[g] + a.my_rank, a.epoch);
+        }
+    }
+}
+
+// =============================================================================================
 // weighted_gather: out_v = Σ_e w_e · θ_src(e)   (self edge reads the live row; in-place safe)
 // =============================================================================================
 struct GatherArgs {
@@ -203,6 +259,46 @@ __global__ void __launch_bounds__(kThreads) nvls_fedavg_kernel(NvlsArgs a) {
             }
             o.x *= a.inv_n; o.y *= a.inv_n; o.z *= a.inv_n; o.w *= a.inv_n;
             *dst = o;
+        }
+    }
+}
+
+// Full-mesh FedAvg on the per-rank sums: T = Σ_ranks rsum_r (one `multimem.ld_reduce` when the arena is bound to an NVLS
+// multicast object and every rank arrived, otherwise G−1 peer loads), then every local node gets T/N — a Byzantine
+// destination swaps its own (attacked) published term for its live row.  Bytes per GPU: one row in over the fabric,
+// V rows written: the minimal-byte schedule ("all destinations share the source set").  Liveness is the frozen mask.
+struct FullMeshArgs {
+    float* live; const float* pub_local; const float* const* peer_rsum; const float* mc_rsum;
+    size_t stride; int V, len4, G, N; const uint8_t* byz; const int* rank_nodes; const uint32_t* timed_out;
+};
+
+__global__ void __launch_bounds__(kThreads) fedavg_fullmesh_kernel(FullMeshArgs a) {
+    const uint32_t dead = a.timed_out ? *a.timed_out : 0u;
+    int n_alive = a.N;
+    if (dead) for (int r = 0; r < a.G; ++r) if ((dead >> r) & 1u) n_alive -= a.rank_nodes[r];
+    const float inv = 1.f / (float)max(n_alive, 1);
+    const bool use_mc = a.mc_rsum != nullptr && dead == 0u && a.G > 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.len4; i += gridDim.x * blockDim.x) {
+        float4 sum;
+        if (use_mc) sum = multimem_ld_reduce_add(a.mc_rsum + ((size_t)i << 2));
+        else {
+            sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < a.G; ++r) {
+                if ((dead >> r) & 1u) continue;
+                const float4 x = ld_stream(reinterpret_cast<const float4*>(a.peer_rsum[r]) + i);
+                sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+            }
+        }
+        for (int v = 0; v < a.V; ++v) {
+            float4 o = sum;
+            float4* dst = reinterpret_cast<float4*>(a.live + (size_t)v * a.stride) + i;
+            if (a.byz[v]) {
+                const float4 p = reinterpret_cast<const float4*>(a.pub_local + (size_t)v * a.stride)[i];
+                const float4 l = *dst;
+                o.x += l.x - p.x; o.y += l.y - p.y; o.z += l.z - p.z; o.w += l.w - p.w;
+            }
+            o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+            st_stream(dst, o);
         }
     }
 }
@@ -862,6 +958,41 @@ void publish(Tensor live, int64_t pub_ptr, int64_t stride, int64_t V, int64_t Pf
     a.ticket = reinterpret_cast<unsigned int*>(ticket.data_ptr<int>());
     dim3 grid(grid_x_for((int)Pf_pad / 4, mb::kThreads, (int)V), (unsigned)V);
     mb::publish_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void publish_sum(Tensor live, int64_t pub_ptr, int64_t rsum_ptr, int64_t stride, int64_t V, int64_t Pf, int64_t Pf_pad,
+                 c10::optional<Tensor> ints, Tensor scale, Tensor noise_std, Tensor node_gid, int64_t seed, int64_t round,
+                 int64_t peer_flags_ptr, int64_t G, int64_t my_rank, int64_t epoch, Tensor ticket) {
+    if (V == 0) return;
+    c10::cuda::CUDAGuard guard(live.device());
+    mb::PublishArgs a;
+    a.live = live.data_ptr<float>(); a.pub = reinterpret_cast<float*>(pub_ptr); a.stride = (size_t)stride;
+    a.Pf = (int)Pf; a.Pf_pad = (int)Pf_pad;
+    a.ints = ints.has_value() && ints->numel() > 0 ? reinterpret_cast<const long long*>(ints->data_ptr<int64_t>()) : nullptr;
+    a.n_int = a.ints ? (int)ints->size(1) : 0;
+    a.scale = scale.data_ptr<float>(); a.noise_std = noise_std.data_ptr<float>(); a.node_gid = node_gid.data_ptr<int>();
+    a.seed = (unsigned long long)seed; a.round = (unsigned long long)round;
+    a.peer_flags = reinterpret_cast<uint32_t* const*>(peer_flags_ptr); a.G = (int)G; a.my_rank = (int)my_rank; a.epoch = (uint32_t)epoch;
+    a.ticket = reinterpret_cast<unsigned int*>(ticket.data_ptr<int>());
+    const int grid = grid_x_for((int)Pf_pad / 4, mb::kThreads, 1);
+    mb::publish_sum_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a, reinterpret_cast<float*>(rsum_ptr), (int)V);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void fedavg_fullmesh(Tensor live, int64_t pub_local_ptr, int64_t peer_rsum_tbl, int64_t mc_rsum_ptr, int64_t stride, int64_t V,
+                     int64_t len, int64_t N, int64_t G, Tensor byz, Tensor rank_nodes, int64_t timed_out_ptr) {
+    if (V == 0) return;
+    c10::cuda::CUDAGuard guard(live.device());
+    TORCH_CHECK(rank_nodes.dtype() == torch::kInt32 && rank_nodes.numel() >= G && byz.numel() >= V);
+    mb::FullMeshArgs a;
+    a.live = live.data_ptr<float>(); a.pub_local = reinterpret_cast<const float*>(pub_local_ptr);
+    a.peer_rsum = reinterpret_cast<const float* const*>(peer_rsum_tbl); a.mc_rsum = reinterpret_cast<const float*>(mc_rsum_ptr);
+    a.stride = (size_t)stride; a.V = (int)V; a.len4 = (int)(len / 4); a.G = (int)G; a.N = (int)N;
+    a.byz = byz.data_ptr<uint8_t>(); a.rank_nodes = rank_nodes.data_ptr<int>();
+    a.timed_out = reinterpret_cast<const uint32_t*>(timed_out_ptr);
+    const int grid = std::max(1, std::min(148 * 8, (a.len4 + mb::kThreads - 1) / mb::kThreads));
+    mb::fedavg_fullmesh_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -14,6 +14,11 @@ void publish(Tensor live, int64_t pub_ptr, int64_t stride, int64_t V, int64_t Pf
 void weighted_gather(Tensor live, int64_t peer_pub_ptr, int64_t parity_off, int64_t stride, int64_t V, Tensor row_ptr,
                      Tensor src_rank, Tensor src_slot, Tensor mask, Tensor w, int64_t len, bool renorm,
                      int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr, bool use_tma);
+void publish_sum(Tensor live, int64_t pub_ptr, int64_t rsum_ptr, int64_t stride, int64_t V, int64_t Pf, int64_t Pf_pad,
+                 c10::optional<Tensor> ints, Tensor scale, Tensor noise_std, Tensor node_gid, int64_t seed, int64_t round,
+                 int64_t peer_flags_ptr, int64_t G, int64_t my_rank, int64_t epoch, Tensor ticket);
+void fedavg_fullmesh(Tensor live, int64_t pub_local_ptr, int64_t peer_rsum_tbl, int64_t mc_rsum_ptr, int64_t stride, int64_t V,
+                     int64_t len, int64_t N, int64_t G, Tensor byz, Tensor rank_nodes, int64_t timed_out_ptr);
 void nvls_fedavg(Tensor live, int64_t pub_local_ptr, int64_t mc_pub_ptr, int64_t stride, int64_t V, int64_t S, int64_t len,
                  int64_t N, Tensor byz, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
 void wait_epoch(Tensor anchor, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
@@ -79,6 +84,8 @@ int64_t conv_gemm(py::dict plan);
 int64_t conv_tma(py::dict plan);
 py::bytes tma_encode(int64_t ptr, std::vector<int64_t> dims, std::vector<int64_t> strides_bytes, std::vector<int64_t> box,
                      std::vector<int64_t> elem_strides, int64_t swizzle);
+void set_pdl(bool on);
+bool get_pdl();
 void gather_grouped(py::dict d);
 void im2col_pack(py::dict d);
 void bn_fwd_grouped(py::dict d);
@@ -99,6 +106,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("tail_blend", &tail_blend);
     m.def("wait_epoch", &wait_epoch);
     m.def("nvls_fedavg", &nvls_fedavg);
+    m.def("publish_sum", &publish_sum, "publish + per-rank column sum of the published rows (full-mesh FedAvg)");
+    m.def("fedavg_fullmesh", &fedavg_fullmesh, "full-mesh FedAvg from the per-rank sums (NVLS multimem.ld_reduce or peer loads)");
     m.def("edge_distances", &edge_distances);
     m.def("pairwise_distances", &pairwise_distances);
     m.def("krum_refine", &krum_refine, "exact fp32 recomputation of the cancellation-prone pairs of a Gram-derived distance table");
@@ -133,6 +142,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("conv_gemm", &conv_gemm, "grouped implicit-GEMM conv / linear layer on tcgen05 (fprop, dgrad, wgrad + SGD)");
     m.def("conv_tma", &conv_tma, "TMA-fed grouped implicit-GEMM conv / linear layer on tcgen05");
     m.def("tma_encode", &tma_encode, "encode a tiled fp32 tensor map (rank <= 5)");
+    m.def("set_pdl", &set_pdl, "enable / disable programmatic dependent launch for the fused tapes");
+    m.def("get_pdl", &get_pdl);
     m.def("gather_grouped", &gather_grouped);
     m.def("im2col_pack", &im2col_pack, "mini-batch gather + im2col of the first layer + per-step packing of its weights");
     m.def("bn_fwd_grouped", &bn_fwd_grouped);

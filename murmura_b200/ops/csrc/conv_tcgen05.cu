@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "conv_common.cuh"
+#include "pdl.cuh"
 
 namespace py = pybind11;
 
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
     __shared__ uint32_t tmem_base_smem;
     __shared__ float bn_ss[2 * BN];
 
+    pdl_launch_dependents();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) CG_STAMP(0);
     const int g = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - g * p.splitk;
     const int m0 = (int)blockIdx.x * kCgBM, n0 = (int)blockIdx.y * BN;
     const int kb_begin = split * p.kb_per_split;
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(kCgThreads) conv_gemm_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    if (tid == 0) CG_STAMP(1);
+    pdl_wait();                                 // predecessor grid complete + flushed: global memory may be touched from here on
+    if (tid == 0) { CG_STAMP(0); CG_STAMP(1); }
 
     float* row = p.row_tab ? reinterpret_cast<float*>(p.row_tab[g]) : p.arena + (long long)(p.gmap ? p.gmap[g] : g) * p.arena_gs;
     float* Wg = row + p.w_off;
@@ -302,8 +304,7 @@ void launch_conv(const mb::ConvGemmParams& p, dim3 grid, cudaStream_t stream) {
         C10_CUDA_CHECK(cudaFuncSetAttribute(mb::conv_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    mb::conv_gemm_kernel<MODE, BN><<<grid, mb::kCgThreads, smem, stream>>>(p);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    C10_CUDA_CHECK(mbhost::launch(mb::conv_gemm_kernel<MODE, BN>, grid, dim3(mb::kCgThreads), smem, stream, dim3(1, 1, 1), p));
 }
 
 }  // namespace

@@ -17,6 +17,7 @@
 #include <c10/cuda/CUDAException.h>
 #include <cuda.h>
 #include "conv_common.cuh"
+#include "pdl.cuh"
 
 namespace py = pybind11;
 
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
     __shared__ uint32_t tmem_base_smem;
     __shared__ float bn_ss[2 * BN];
 
+    pdl_launch_dependents();                    // the next kernel's prologue may overlap this one (it blocks in pdl_wait)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - g * p.splitk;
     const int n0 = (int)blockIdx.y * BN;
@@ -78,7 +80,6 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
     const TapClass& cls = P.cls[ci];
     const int kb_total = MODE == kModeW ? p.kb_total : cls.ntaps * (p.C / kCgBK);
     const int nkb = max(0, min(kb_total, kb_begin + p.kb_per_split) - kb_begin);    // 0: nothing to add for this slice
-    const int slot = p.gmap ? p.gmap[g] : g;
     const uint32_t smem0 = smem_u32(smem);
 
     if (warp == 4) {
@@ -112,6 +113,8 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();                                 // predecessor grid complete + flushed: global memory may be touched from here on
+    const int slot = p.gmap ? p.gmap[g] : g;
 
     // tile origin in the row space of modes F / D
     int b0 = 0, y0 = 0;
@@ -239,8 +242,7 @@ void launch_tma(const mb::ConvTmaParams& P, dim3 grid, cudaStream_t stream) {
         C10_CUDA_CHECK(cudaFuncSetAttribute(mb::conv_tma_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    mb::conv_tma_kernel<MODE, BN><<<grid, mb::kCtThreads, smem, stream>>>(P);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    C10_CUDA_CHECK(mbhost::launch(mb::conv_tma_kernel<MODE, BN>, grid, dim3(mb::kCtThreads), smem, stream, dim3(1, 1, 1), P));
 }
 }  // namespace
 

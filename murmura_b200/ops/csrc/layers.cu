@@ -13,6 +13,7 @@
 #include <c10/cuda/CUDAException.h>
 #include <pybind11/pybind11.h>
 #include "common.cuh"
+#include "pdl.cuh"
 
 namespace cg = cooperative_groups;
 namespace py = pybind11;
@@ -44,6 +45,7 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) gather_grouped_kernel(GatherArgs a) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     const int g = blockIdx.z, r = blockIdx.y;
     const int slot = a.gmap ? a.gmap[g] : g;
     const long long src = a.perm[(long long)slot * a.perm_ld + (long long)a.t * a.eb + r];
@@ -89,6 +91,7 @@ struct Im2colArgs {
 };
 
 __global__ void __launch_bounds__(256) im2col_pack_kernel(Im2colArgs a) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     extern __shared__ int ktab[];                            // k → (kh << 24 | kw << 16 | c), −1 for the padding columns
     const int g = blockIdx.z, r = blockIdx.y;
     const int K4 = a.Kpad >> 2;
@@ -219,6 +222,7 @@ __device__ __forceinline__ void gbn_cluster_fold(cg::cluster_group& cluster, flo
 
 template <int TC>
 __global__ void __launch_bounds__(kGbnThreads) gbn_fwd_kernel(GbnFwdArgs a) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     constexpr int Q = TC / 4, RL = kGbnThreads / Q;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float wpart[kGbnThreads / 32][4][8];
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(kGbnThreads) gbn_fwd_kernel(GbnFwdArgs a) {
 // dy → (dropout) → (ReLU mask from y) → dz;  dres = dz;  dx = γ·istd·(dz − mean(dz) − x̂·mean(dz·x̂));  γ −= lr·Σdz·x̂, β −= lr·Σdz
 template <int TC>
 __global__ void __launch_bounds__(kGbnThreads) gbn_bwd_kernel(GbnBwdArgs a) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     constexpr int Q = TC / 4, RL = kGbnThreads / Q;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float wpart[kGbnThreads / 32][4][8];
@@ -402,6 +407,7 @@ __device__ __forceinline__ long long pool_out_index(const PoolArgs& a, int b, in
 
 // one thread = 4 consecutive channels of one output pixel (float4 loads / stores; no per-element div/mod chains)
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolArgs a) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     const int g = blockIdx.y;
     const int C4 = a.C >> 2;
     const long long total = (long long)a.B * a.OH * a.OW * C4;
@@ -447,6 +453,7 @@ struct PoolBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolBwdArgs a) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     const int g = blockIdx.y;
     const int C4 = a.C >> 2;
     const long long total = (long long)a.B * a.H * a.W * C4;
@@ -495,6 +502,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolBwdArgs a) {
 
 // ---- global average pooling [B][HW][C] ↔ [B][C] ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* x, long long x_gs, float* y, long long y_gs, int B, int HW, int C) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     const int g = blockIdx.y;
     const float inv = 1.f / (float)HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * C; i += (long long)gridDim.x * blockDim.x) {
@@ -506,6 +514,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* x, long l
     }
 }
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* dy, long long dy_gs, float* dx, long long dx_gs, int B, int HW, int C) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     const int g = blockIdx.y;
     const float inv = 1.f / (float)HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * HW * C; i += (long long)gridDim.x * blockDim.x) {
@@ -517,6 +526,7 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* dy, long 
 // ---- stand-alone dropout (models that apply it after a plain ReLU) ------------------------------------------------------
 __global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* y, const float* mask, long long x_gs, long long y_gs, long long m_gs, long long n4, const int* gmap,
                                                       const long long* rng_step, unsigned long long seed, int layer_id, float p_drop) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     const int g = blockIdx.y;
     const int slot = gmap ? gmap[g] : g;
     const uint64_t stream = ((uint64_t)(*rng_step) << 24) ^ ((uint64_t)layer_id << 12) ^ (uint64_t)slot;
@@ -551,6 +561,7 @@ __device__ __forceinline__ float gl_trigamma(float x) {
 // softmax cross-entropy, mean over the batch: grad[b][c] = (softmax − onehot)/B, padding columns [C, ld) are written as 0
 __global__ void __launch_bounds__(256) ce_loss_grouped_kernel(const float* logits, long long gs, const long long* targets, long long t_gs,
                                                               float* grad, long long grad_gs, float* loss_acc, const int* gmap, int B, int C, int ld) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     __shared__ float wsum[8];
     const int g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -585,6 +596,7 @@ __global__ void __launch_bounds__(256) ce_loss_grouped_kernel(const float* logit
 __global__ void __launch_bounds__(256) evidential_loss_grouped_kernel(const float* alpha, long long gs, const long long* targets, long long t_gs,
                                                                       float* grad, long long grad_gs, float* loss_acc, const int* gmap, const float* lam_ptr,
                                                                       int B, int C, int ld) {
+    pdl_launch_dependents(); pdl_wait();        // PDL: see pdl.cuh (no prologue worth overlapping here, only the launch latency)
     __shared__ float wsum[8];
     const int g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -648,20 +660,20 @@ int gs_blocks(long long n, int G) { return (int)std::max<long long>(1, std::min<
 int gbn_row_splits(int M) { int s = 1; while (s < 8 && M > 256 * s) s <<= 1; return s; }
 bool gbn_narrow(int C, int M, int G) { return ((C + 15) / 16) * gbn_row_splits(M) * G < 96; }
 
+template <typename... P, typename... A>
+void llaunch(void (*kernel)(P...), dim3 grid, size_t smem, A&&... args) {
+    C10_CUDA_CHECK(mbhost::launch(kernel, grid, dim3(256), smem, lstream(), dim3(1, 1, 1), std::forward<A>(args)...));
+}
+
 template <typename Args>
 void gbn_launch(void (*kernel)(Args), const Args& a, int C, int M, int tile, int G) {
-    cudaLaunchConfig_t cfg = {};
     const int splits = gbn_row_splits(M);
-    cfg.gridDim = dim3((C + tile - 1) / tile, splits, G);
-    cfg.blockDim = dim3(mb::kGbnThreads, 1, 1);
-    cfg.stream = lstream();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = splits; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    C10_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, a));
+    C10_CUDA_CHECK(mbhost::launch(kernel, dim3((C + tile - 1) / tile, splits, G), dim3(mb::kGbnThreads), 0, lstream(), dim3(1, splits, 1), a));
 }
 }  // namespace
+
+void set_pdl(bool on) { mbhost::pdl_flag() = on; }      // A/B switch for programmatic dependent launch (default on)
+bool get_pdl() { return mbhost::pdl_flag(); }
 
 void gather_grouped(py::dict d) {
     mb::GatherArgs a;
@@ -677,7 +689,7 @@ void gather_grouped(py::dict d) {
     TORCH_CHECK(G >= 1 && a.eb >= 1 && a.Cdst >= a.Csrc && (a.rng_step == nullptr || a.ticket != nullptr));
     const long long row = (long long)a.npix * a.Cdst;
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(8, (row / 4 + 255) / 256)), (unsigned)a.eb, (unsigned)G);
-    mb::gather_grouped_kernel<<<grid, 256, 0, lstream()>>>(a);
+    llaunch(mb::gather_grouped_kernel, grid, 0, a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -702,7 +714,7 @@ void im2col_pack(py::dict d) {
     TORCH_CHECK(a.Cin < 65536 && a.KW < 256 && a.KH < 128 && a.Kpad * 4 <= 48 * 1024, "im2col_pack: first-layer geometry out of range");
     const long long pix = (long long)a.OH * a.OW;                          // 8 warps per block, one output pixel per warp pass
     dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(16, (pix + 7) / 8)), (unsigned)(a.eb + (a.wpack ? 1 : 0)), (unsigned)G);
-    mb::im2col_pack_kernel<<<grid, 256, a.Kpad * sizeof(int), lstream()>>>(a);
+    llaunch(mb::im2col_pack_kernel, grid, a.Kpad * sizeof(int), a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -754,7 +766,7 @@ void maxpool_fwd_grouped(py::dict d) {
     const int G = d["G"].cast<int>();
     TORCH_CHECK(a.k * a.k < 255 && a.C % 4 == 0, "maxpool: C must be a multiple of 4");
     dim3 grid(gs_blocks((long long)a.B * a.OH * a.OW * (a.C / 4), G), G);
-    mb::maxpool_fwd_kernel<<<grid, 256, 0, lstream()>>>(a);
+    llaunch(mb::maxpool_fwd_kernel, grid, 0, a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -768,7 +780,7 @@ void maxpool_bwd_grouped(py::dict d) {
     const int G = d["G"].cast<int>();
     TORCH_CHECK(a.C % 4 == 0);
     dim3 grid(gs_blocks((long long)a.B * a.H * a.W * (a.C / 4), G), G);
-    mb::maxpool_bwd_kernel<<<grid, 256, 0, lstream()>>>(a);
+    llaunch(mb::maxpool_bwd_kernel, grid, 0, a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -777,10 +789,10 @@ void avgpool_grouped(py::dict d) {
     const bool bwd = lget<int>(d, "backward", 0) != 0;
     if (!bwd) {
         dim3 grid(gs_blocks((long long)B * C, G), G);
-        mb::avgpool_fwd_kernel<<<grid, 256, 0, lstream()>>>(lptr<const float>(d, "x"), d["x_gs"].cast<int64_t>(), lptr<float>(d, "y"), d["y_gs"].cast<int64_t>(), B, HW, C);
+        llaunch(mb::avgpool_fwd_kernel, grid, 0, lptr<const float>(d, "x"), d["x_gs"].cast<int64_t>(), lptr<float>(d, "y"), d["y_gs"].cast<int64_t>(), B, HW, C);
     } else {
         dim3 grid(gs_blocks((long long)B * HW * C, G), G);
-        mb::avgpool_bwd_kernel<<<grid, 256, 0, lstream()>>>(lptr<const float>(d, "dy"), d["dy_gs"].cast<int64_t>(), lptr<float>(d, "dx"), d["dx_gs"].cast<int64_t>(), B, HW, C);
+        llaunch(mb::avgpool_bwd_kernel, grid, 0, lptr<const float>(d, "dy"), d["dy_gs"].cast<int64_t>(), lptr<float>(d, "dx"), d["dx_gs"].cast<int64_t>(), B, HW, C);
     }
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
@@ -790,7 +802,7 @@ void dropout_grouped(py::dict d) {
     const long long n = d["n"].cast<int64_t>();
     TORCH_CHECK(n % 4 == 0);
     dim3 grid(gs_blocks(n / 4, G), G);
-    mb::dropout_kernel<<<grid, 256, 0, lstream()>>>(lptr<const float>(d, "x"), lptr<float>(d, "y"), lptr<const float>(d, "mask"), d["x_gs"].cast<int64_t>(), d["y_gs"].cast<int64_t>(), lget<int64_t>(d, "m_gs", 0), n / 4, lptr<const int>(d, "gmap"),
+    llaunch(mb::dropout_kernel, grid, 0, lptr<const float>(d, "x"), lptr<float>(d, "y"), lptr<const float>(d, "mask"), d["x_gs"].cast<int64_t>(), d["y_gs"].cast<int64_t>(), lget<int64_t>(d, "m_gs", 0), n / 4, lptr<const int>(d, "gmap"),
                                                     lptr<const long long>(d, "rng_step"), (unsigned long long)lget<int64_t>(d, "seed", 0),
                                                     lget<int>(d, "layer_id", 0), d["p_drop"].cast<float>());
     C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -801,10 +813,10 @@ void loss_grouped(py::dict d) {
     const bool evidential = lget<int>(d, "evidential", 0) != 0;
     TORCH_CHECK(B > 0 && C > 0 && ld >= C);
     if (evidential)
-        mb::evidential_loss_grouped_kernel<<<G, 256, 0, lstream()>>>(lptr<const float>(d, "out"), d["gs"].cast<int64_t>(), lptr<const long long>(d, "targets"),
+        llaunch(mb::evidential_loss_grouped_kernel, G, 0, lptr<const float>(d, "out"), d["gs"].cast<int64_t>(), lptr<const long long>(d, "targets"),
             d["t_gs"].cast<int64_t>(), lptr<float>(d, "grad"), lget<int64_t>(d, "grad_gs", d["gs"].cast<int64_t>()), lptr<float>(d, "loss_acc"), lptr<const int>(d, "gmap"), lptr<const float>(d, "lam"), B, C, ld);
     else
-        mb::ce_loss_grouped_kernel<<<G, 256, 0, lstream()>>>(lptr<const float>(d, "out"), d["gs"].cast<int64_t>(), lptr<const long long>(d, "targets"),
+        llaunch(mb::ce_loss_grouped_kernel, G, 0, lptr<const float>(d, "out"), d["gs"].cast<int64_t>(), lptr<const long long>(d, "targets"),
             d["t_gs"].cast<int64_t>(), lptr<float>(d, "grad"), lget<int64_t>(d, "grad_gs", d["gs"].cast<int64_t>()), lptr<float>(d, "loss_acc"), lptr<const int>(d, "gmap"), B, C, ld);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

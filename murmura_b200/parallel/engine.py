@@ -784,11 +784,19 @@ class B200Network:
             return 0, self.world, 0, 0.0, self.arena.timed_out_ptr()
         return self.arena.flags_ptr(), self.world, self.epoch, float(self.opt.flag_timeout_ms), self.arena.timed_out_ptr()
 
-    def _publish(self, parity: int) -> None:
+    def _publish(self, parity: int, with_sum: bool = False) -> None:
         L = self.layout
         self.epoch += 1
         if self.custom_attack:
             self._publish_custom(parity)
+        if with_sum and self.V:
+            # full-mesh FedAvg: the publish pass also leaves Σ_v published_v in this rank's rsum row
+            self.ext.publish_sum(self.live, self.arena.pub_plane_ptr(parity), self.arena.rsum_ptr(parity), L.stride, self.V, L.Pf, L.Pf_pad,
+                                 self.ints if L.Pi else None, self.atk_scale, self.atk_noise, self.node_gid,
+                                 int(self.cfg.experiment.seed), int(self.round_idx),
+                                 self.arena.tbl_flags.data_ptr() if self.world > 1 else 0, self.world, self.rank, self.epoch, self.ticket)
+            self.kernel_launches += 1
+            return
         if self.V == 0:                         # a rank hosting no node still has to raise its epoch flag
             self.ext.publish(self.live, self.arena.pub_plane_ptr(parity), L.stride, 1, 0, 0, None, self.atk_scale,
                              self.atk_noise, self.node_gid, 0, 0, self.arena.tbl_flags.data_ptr() if self.world > 1 else 0,
@@ -844,12 +852,32 @@ class B200Network:
         self._stat_log.append(et["stats"][: self.V].clone())
 
     # ---- FedAvg ------------------------------------------------------------------------------
+    def _fullmesh_fedavg(self, et) -> bool:
+        """True when every node averages the SAME set (fully connected FedAvg, no dropped edges, device-side attack): the
+        round then moves one per-rank sum row instead of every node's row (``publish_sum`` → ``fedavg_fullmesh``)."""
+        if self.family != "fedavg" or self.custom_attack or self.opt.fault_drop_edges or self.opt.transport == "nccl":
+            return False
+        if "full_mesh" not in et:
+            rows = et["host_rows"]
+            et["full_mesh"] = all(rows[i + 1] - rows[i] == self.N for i in range(len(rows) - 1))
+        return bool(et["full_mesh"]) and self.opt.fullmesh_rank_sum
+
     def _agg_fedavg(self, et, parity: int) -> None:
         if "fedavg_ready" not in et:
             self.ext.fedavg_weights(*self._et_args(et)); et["fedavg_ready"] = True
             rows = et["host_rows"]
             et["full_mesh"] = all(rows[i + 1] - rows[i] == self.N for i in range(len(rows) - 1))
             et["byz"] = torch.tensor([1 if vn.byzantine else 0 for vn in self.nodes] or [0], dtype=torch.uint8, device=self.device)
+        if et.get("rank_sum"):
+            if not hasattr(self, "_rank_nodes"):
+                self._rank_nodes = torch.tensor([int(c) for c in self.placement.counts] + [0] * 16, dtype=torch.int32, device=self.device)[: max(self.world, 1)].contiguous()
+            L = self.layout
+            use_mc = self.opt.transport == "nvls" and self.world > 1 and self.arena.mc_base
+            self.ext.fedavg_fullmesh(self.live, self.arena.pub_plane_ptr(parity), self.arena.tbl_rsum[parity].data_ptr(),
+                                     self.arena.mc_rsum_ptr(parity) if use_mc else 0, L.stride, self.V, L.Pf_pad, self.N, self.world,
+                                     et["byz"], self._rank_nodes, self._sync_args()[4])
+            self.kernel_launches += 1
+            return                                            # int buffers keep own under FedAvg: nothing to blend
         if (self.opt.transport == "nvls" and self.world > 1 and et["full_mesh"] and self.arena.mc_base
                 and not self.opt.fault_drop_edges):
             # full mesh ⇒ every node computes the same mean: let the NVSwitch do the cross-GPU sum (multimem.ld_reduce)
@@ -1352,7 +1380,8 @@ class B200Network:
         if self.world > 1:
             self.arena.timed_out.zero_()
             self._liveness_frozen = False
-        self._publish(parity)
+        et["rank_sum"] = self._fullmesh_fedavg(et)
+        self._publish(parity, with_sum=et["rank_sum"])
         self._freeze_liveness()
         if self.family == "ubar":
             self._ubar_prepare(et, parity)
@@ -1372,6 +1401,13 @@ class B200Network:
         edges = len(rk)
         remote = sum(1 for r in rk if r != self.rank)
         row = self.layout.Pf_pad * 4
+        if et.get("rank_sum"):
+            # publish_sum: V rows read, V + 1 written; fedavg_fullmesh: own sum row read, V rows written; fabric: one row per peer
+            # (or ONE multicast row when the NVSwitch reduces)
+            nvls = self.opt.transport == "nvls" and self.arena.mc_base
+            self.timers["hbm_bytes"] = self.timers.get("hbm_bytes", 0.0) + row * (3 * self.V + 2)
+            self.timers["nvlink_bytes"] = self.timers.get("nvlink_bytes", 0.0) + row * (0 if self.world == 1 else (1 if nvls else self.world - 1))
+            return
         passes = 1.0 + self._FILTER_ROW_PASSES.get(self.family, 0.0)
         extra = self.V if self.family == "sketchguard" else (self.N / max(self.world, 1) if self.family == "krum" else 0.0)
         self.timers["hbm_bytes"] = self.timers.get("hbm_bytes", 0.0) + row * (3 * self.V + passes * (edges - remote) + extra)
@@ -1406,7 +1442,10 @@ class B200Network:
             return None
         shape = (first.X.shape[3], first.X.shape[1], first.X.shape[2]) if first.X.dim() == 4 else tuple(first.X.shape[1:])
         n_max = max(vn.n for vn in self.nodes)
-        EB = min(max(32, int(self.opt.fused_eval_rows)), (n_max + 31) // 32 * 32)
+        # rows per group and launch: ≥ fused_eval_rows, and ≈ 2048 rows per launch over all groups so that a GPU hosting one or
+        # two nodes (launch-latency bound) evaluates its shard in one or two passes instead of many small ones
+        EB = max(32, int(self.opt.fused_eval_rows), (2048 // max(self.V, 1) + 31) // 32 * 32)
+        EB = min(EB, (n_max + 31) // 32 * 32)
         fe = FusedForward(first.model, self.layout, self.live, EB, shape, self.V, evidential=self.evidential)
         if not fe.supported or (self.evidential and not fe.evidential_head):
             return None

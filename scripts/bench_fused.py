@@ -63,13 +63,50 @@ def per_op(tr, G, lr=0.01):
     return rows
 
 
+def timeline(name, G, side, out_path):
+    """CUPTI records of one graph replay: per-kernel start/duration, busy time vs wall time (ranking only — profiler overhead)."""
+    from torch.profiler import ProfilerActivity, profile
+    steps = 4
+    tr = build(name, G, steps, side)
+    tr.refresh_permutations(1); tr._capture(0.01)
+    for _ in range(3):
+        tr.graph.replay()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        tr.graph.replay(); torch.cuda.synchronize()
+    evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start
+    wall = evs[-1].time_range.end - t0
+    busy, cur_end, rows = 0.0, t0, []
+    for e in evs:
+        s, t = e.time_range.start, e.time_range.end
+        busy += max(0.0, t - max(s, cur_end)); cur_end = max(cur_end, t)
+        rows.append((round(s - t0, 2), round(t - s, 2), e.name[:70]))
+    agg = {}
+    for _, d, n in rows:
+        a = agg.setdefault(n, [0.0, 0]); a[0] += d; a[1] += 1
+    res = {"model": name, "G": G, "side": side, "steps": steps, "wall_us_per_step": wall / steps, "busy_us_per_step": busy / steps,
+           "kernels_per_step": len(rows) / steps,
+           "by_kernel": {n: {"us_per_step": round(v[0] / steps, 1), "n_per_step": v[1] / steps, "avg_us": round(v[0] / v[1], 2)} for n, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+           "first_step": rows[: len(rows) // steps]}
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(res, open(out_path, "w"), indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k not in ("first_step",)}, indent=1))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--timeline", type=int, default=0, help="G: dump the CUPTI kernel timeline of one graph replay")
     ap.add_argument("--out", default="gpurun_out/bench_fused.json")
     ap.add_argument("--model", default="resnet18")
     ap.add_argument("--target-ctas", type=int, default=148)
     ap.add_argument("--quick", action="store_true", help="graph timings only (no eager per-launch pass)")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch on / off (A/B)")
     args = ap.parse_args()
+    from murmura_b200 import ops
+    ops.load(required=True).set_pdl(bool(args.pdl))
+    if args.timeline:
+        return timeline(args.model, args.timeline, True, args.out)
     out = {"model": args.model, "runs": []}
     for G in (1, 8):
         for side in (False, True):

@@ -114,6 +114,26 @@ def test_fused_aggregation_matches_cpu_oracle_bn_model(algo, params, attack):
         net.close()
 
 
+@pytest.mark.parametrize("attack", [None, {"enabled": True, "type": "directed_deviation", "percentage": 0.34, "params": {"lambda_param": -5.0}},
+                                    {"enabled": True, "type": "gaussian", "percentage": 0.34, "params": {"noise_std": 0.5}}])
+def test_fullmesh_rank_sum_fedavg_matches_cpu_oracle(attack):
+    """Fully connected FedAvg takes the publish_sum → fedavg_fullmesh path (one per-rank sum row); same result as the reference
+    aggregator on the published states, and as the general edge-list gather."""
+    outs = []
+    for rank_sum in (True, False):
+        cfg = _cfg("fedavg", {}, n=6, topo={"type": "fully", "num_nodes": 6}, attack=attack, model=HAR, data=HAR_DATA,
+                   b200={"fullmesh_rank_sum": rank_sum})
+        net, adapter, mf = _build(cfg)
+        try:
+            got, want, own, pub = _oracle_round(net, cfg, adapter, mf)
+            _assert_states_close(got, want)
+            assert bool(net._last_et.get("rank_sum")) == rank_sum
+            outs.append(got)
+        finally:
+            net.close()
+    _assert_states_close(outs[0], outs[1])
+
+
 def test_fused_evidential_trust_matches_cpu_oracle():
     cfg = _cfg("evidential_trust", {"trust_threshold": 0.05, "self_weight": 0.6, "accuracy_weight": 0.7}, n=5,
                topo={"type": "fully", "num_nodes": 5}, model=HAR, data=HAR_DATA, b200={"grouped_mlp": False})
