@@ -22,6 +22,8 @@
 namespace cg = cooperative_groups;
 using torch::Tensor;
 
+#include "common.cuh"
+
 namespace mb {
 
 constexpr int kBnThreads = 256;      // (TC/4) channel quads × (1024/TC) row lanes; TC = channels per CTA:
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_act_fwd_kernel(BnFwdArgs a) {
         float4 v = ld4(a.x + o);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         if (a.res) { const float4 t = ld4(a.res + o); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (a.relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
         st4(a.y + o, v);
     }
 }

@@ -36,6 +36,10 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// ReLU that propagates NaN like torch.relu (fmaxf would launder a NaN — e.g. from an attacked, negative running variance — into 0,
+// and a poisoned candidate would then score a finite loss where the reference scores NaN and rejects it).
+__device__ __forceinline__ float relu_nan(float x) { return x < 0.f ? 0.f : x; }
+
 // ---- reductions ----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

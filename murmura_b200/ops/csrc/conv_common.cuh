@@ -102,7 +102,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmParams& p, uint32_t 
                     float x = f[i];
                     if (bn) x = fmaf(x, ss[c0 + i], ss[BN + c0 + i]);
                     if (rrow) { if (mask) x = rrow[col] > 0.f ? x : 0.f; else x += rrow[col]; }
-                    if (relu) x = fmaxf(x, 0.f);
+                    if (relu) x = relu_keep_nan(x);
                     else if (act2) x = (x > 20.f ? x : log1pf(__expf(x))) + 1.f;       // Dirichlet head: softplus + 1
                     f[i] = x;
                 }

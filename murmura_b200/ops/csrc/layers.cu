@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kGbnThreads) gbn_fwd_kernel(GbnFwdArgs a) {
         float4 v = gld4(x + o);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         if (res) { const float4 t = gld4(res + o); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (a.relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
         if (drop) { const float4 k = dropout_scale4(a.seed, stream, o >> 2, a.p_drop); v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w; }
         gst4(y + o, v);
     }
@@ -428,10 +428,10 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolArgs a) {
                 if (iw < 0 || iw >= a.W) continue;
                 const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * a.H + ih) * a.W + iw) * a.C + c);
                 const int tap = kh * a.k + kw;                                   // first maximum in scan order (ATen's rule)
-                if (v.x > best.x || arg.x == 255) { best.x = v.x; arg.x = tap; }
-                if (v.y > best.y || arg.y == 255) { best.y = v.y; arg.y = tap; }
-                if (v.z > best.z || arg.z == 255) { best.z = v.z; arg.z = tap; }
-                if (v.w > best.w || arg.w == 255) { best.w = v.w; arg.w = tap; }
+                if (v.x > best.x || v.x != v.x || arg.x == 255) { best.x = v.x; arg.x = tap; }
+                if (v.y > best.y || v.y != v.y || arg.y == 255) { best.y = v.y; arg.y = tap; }
+                if (v.z > best.z || v.z != v.z || arg.z == 255) { best.z = v.z; arg.z = tap; }
+                if (v.w > best.w || v.w != v.w || arg.w == 255) { best.w = v.w; arg.w = tap; }
             }
         }
         const long long o = (((long long)b * a.OH + oh) * a.OW + ow) * a.C + c;     // NHWC position (also the index-map position)

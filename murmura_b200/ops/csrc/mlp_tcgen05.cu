@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kLinThreads) grouped_linear_tf32_kernel(const 
                 float v = __uint_as_float(r[j]);
                 if (g.bias) v += g.bias[n];
                 if (g.bn_mean) v = (v - g.bn_mean[n]) * rsqrtf(g.bn_var[n] + eps) * (g.bn_gamma ? g.bn_gamma[n] : 1.f) + (g.bn_beta ? g.bn_beta[n] : 0.f);
-                if (act == 1) v = fmaxf(v, 0.f);
+                if (act == 1) v = v < 0.f ? 0.f : v;        // NaN-propagating ReLU (torch.relu semantics)
                 else if (act == 2) v = (v > 20.f ? v : log1pf(expf(v))) + 1.f;          // Dirichlet head: softplus + 1
                 g.Y[row * ldy + n] = v;
             }

@@ -116,4 +116,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ReLU that propagates NaN like torch.relu (see common.cuh).
+__device__ __forceinline__ float relu_keep_nan(float x) { return x < 0.f ? 0.f : x; }
+
 }  // namespace mbtc

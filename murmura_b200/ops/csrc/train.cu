@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
             v.x = (v.x - m.x) * rsqrtf(s2.x + eps) * g.x + b.x; v.y = (v.y - m.y) * rsqrtf(s2.y + eps) * g.y + b.y;
             v.z = (v.z - m.z) * rsqrtf(s2.z + eps) * g.z + b.z; v.w = (v.w - m.w) * rsqrtf(s2.w + eps) * g.w + b.w;
             if (res) { const float4 t = reinterpret_cast<const float4*>(res)[i]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
             reinterpret_cast<float4*>(y)[i] = v;
         }
         return;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const float* __restrict__ 
         const int c = (int)((i / inner) % C);
         float v = (x[i] - mean[c]) * rsqrtf(var[c] + eps) * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
         if (res) v += res[i];
-        y[i] = relu ? fmaxf(v, 0.f) : v;
+        y[i] = relu ? relu_nan(v) : v;
     }
 }
 

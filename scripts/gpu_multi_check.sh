@@ -16,3 +16,4 @@ except Exception as e: print('ERR $impl $c rc=$rc', e)
 PY
   done
 done
+timeout 300 $TR --master-port 29599 scripts/p2p_bench.py > gpurun_out/p2p_bench_${N}gpu.log 2>&1; echo "p2p rc=$?"; grep -c kernel gpurun_out/p2p_bench_${N}gpu.log

@@ -86,7 +86,11 @@ def check(algo, params, n, topo, b200=None, attack=ATTACK, rounds=2, tol=5e-5):
                         dbg = {"gids": et["host_gid"][e0:e1], "w": et["w"][e0:e1].tolist(), "dist": et["dist"][e0:e1].tolist(),
                                "stats": et["stats"][vi].tolist(), "cpu_thr": getattr(cpu_aggs[vn.gid], "threshold_history", [None])[-1:],
                                "cpu_scores": {j: v[-1] for j, v in getattr(cpu_aggs[vn.gid], "neighbor_scores", {}).items()},
-                               "byz": sorted(net.compromised)}
+                               "byz": sorted(net.compromised),
+                               "gpu_cand": et["aux"][e0:e1].tolist() if "aux" in et else None, "gpu_loss": et["aux3"][e0:e1].tolist() if "aux3" in et else None,
+                               "gpu_own_loss": et["n2"][vi].item() if "n2" in et else None, "gpu_d2": et["d2"][e0:e1].tolist() if "d2" in et else None,
+                               "cpu_losses": {j: v[-1] for j, v in getattr(cpu_aggs[vn.gid], "neighbor_losses", {}).items() if v},
+                               "cpu_dist": {j: v[-1] for j, v in getattr(cpu_aggs[vn.gid], "neighbor_distances", {}).items() if v}}
                         raise AssertionError(f"[{algo}] rank {rank} node {vn.gid} key {k} round {r}: max err {err}\n  debug: {dbg}")
                 elif not torch.equal(gk.long(), w.long()):
                     raise AssertionError(f"[{algo}] rank {rank} node {vn.gid} int key {k}: {gk} vs {w}")
@@ -123,6 +127,10 @@ def main():
         check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"transport": "nvls"})
         check("fedavg", {}, n, {"type": "ring", "num_nodes": n}, b200={"transport": "nvls"})
         check("krum", {"num_compromised": 1}, n, {"type": "k-regular", "num_nodes": n, "k": 4}, b200={"transport": "nvls", "krum_gram": "tcgen05"})
+        dist.barrier(); dist.destroy_process_group(); return
+    if only == "ubar":
+        check("ubar", {"rho": 0.6, "alpha": 0.5}, n, {"type": "k-regular", "num_nodes": n, "k": 4}, b200={"grouped_mlp": False})
+        check("ubar", {"rho": 0.6, "alpha": 0.5}, n, {"type": "k-regular", "num_nodes": n, "k": 4}, b200={"grouped_mlp": False, "fused_train": False})
         dist.barrier(); dist.destroy_process_group(); return
     if only == "sketch":
         kreg = {"type": "k-regular", "num_nodes": n, "k": 4}

@@ -18,10 +18,10 @@ rank, world, _ = init_distributed()
 n = 8 if world <= 8 else world
 
 
-def build(transport, topo, gather="ldg"):
+def build(transport, topo, gather="ldg", rank_sum=True):
     cfg = Config(**{"experiment": {"name": "p2p", "rounds": 4, "seed": 1}, "topology": topo, "aggregation": {"algorithm": "fedavg"},
                     "training": {"batch_size": 16, "lr": 0.01}, "data": {"adapter": "synthetic.cifar10", "params": {"samples_per_node": 16, "partition_method": "iid"}},
-                    "model": {"factory": "models.resnet18"}, "backend": "b200", "b200": {"transport": transport, "placement": "contiguous", "cuda_graphs": False, "gather_impl": gather}})
+                    "model": {"factory": "models.resnet18"}, "backend": "b200", "b200": {"transport": transport, "placement": "contiguous", "cuda_graphs": False, "gather_impl": gather, "fullmesh_rank_sum": rank_sum}})
     ad = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
     return Network.from_config(cfg, mf, ad, build_aggregator_factory(cfg, mf))
 
@@ -36,8 +36,10 @@ def timed(net, reps=12):
         parity = r & 1
         neighbors, key = net._neighbors_for_round(r)
         et = net._edge_table(neighbors, key)
-        net._publish(parity)
-        net._host_wait_epoch(); torch.cuda.synchronize(); dist.barrier()
+        et["rank_sum"] = net._fullmesh_fedavg(et)
+        net._liveness_frozen = False
+        net._publish(parity, with_sum=et["rank_sum"])
+        net._freeze_liveness(); torch.cuda.synchronize(); dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); net._agg_fedavg(et, parity); b.record(); torch.cuda.synchronize()
         if r >= 3:
@@ -47,21 +49,30 @@ def timed(net, reps=12):
 
 
 out = []
-for transport, topo_name, gather in (("p2p", "fully", "ldg"), ("p2p", "fully", "tma"), ("nvls", "fully", "ldg"), ("p2p", "ring", "ldg"), ("p2p", "ring", "tma")):
+for transport, topo_name, gather, rank_sum in (("p2p", "fully", "ldg", True), ("nvls", "fully", "ldg", True), ("p2p", "fully", "ldg", False),
+                                              ("p2p", "fully", "tma", False), ("nvls", "fully", "ldg", False), ("p2p", "ring", "ldg", False),
+                                              ("p2p", "ring", "tma", False)):
     topo = {"type": topo_name, "num_nodes": n}
-    net = build(transport, topo, gather)
+    net = build(transport, topo, gather, rank_sum)
     ms = timed(net)
     L, pl = net.layout, net.placement
     remote = sum(1 for vn in net.nodes for j in net.topology.neighbors[vn.gid] if pl.rank_of[j] != net.rank)
     local = sum(1 for vn in net.nodes for j in net.topology.neighbors[vn.gid] if pl.rank_of[j] == net.rank) + len(net.nodes)
     row = L.Pf_pad * 4
-    if transport == "nvls" and topo_name == "fully":
+    if rank_sum and topo_name == "fully":
+        if transport == "nvls":
+            link_bytes = row * (world - 1) / world
+            note = "per-rank sum rows, multimem.ld_reduce: ONE reduced row per GPU"
+        else:
+            link_bytes = row * (world - 1)
+            note = f"per-rank sum rows: {world - 1} peer rows read per GPU"
+    elif transport == "nvls" and topo_name == "fully":
         link_bytes = net.S * row * (world - 1) / world            # in-switch reduction: each GPU ingests S reduced rows (own share stays local)
         note = "multimem.ld_reduce: the switch sums the ranks' copies"
     else:
         link_bytes = remote * row
         note = f"{remote} remote + {local} local row reads per GPU"
-    rec = {"kernel": f"fedavg exchange+aggregate ({transport}, {topo_name}, gather={gather})", "gpus": world, "nodes": n, "ms": round(ms, 4),
+    rec = {"kernel": f"fedavg exchange+aggregate ({transport}, {topo_name}, gather={gather}, rank_sum={rank_sum and topo_name == 'fully'})", "gpus": world, "nodes": n, "ms": round(ms, 4),
            "nvlink_GB_per_gpu": round(link_bytes / 1e9, 4), "nvlink_GBps": round(link_bytes / ms / 1e6, 1),
            "frac_of_measured_nvlink": round(link_bytes / ms / 1e6 / NVLINK_GBS, 3), "note": note}
     out.append(rec)

@@ -47,6 +47,8 @@ def _oracle_round(net, cfg, adapter, mf, parity=0):
     for vn in net.nodes:                                             # decorrelate node states + non-trivial int buffers
         for e in L.float_entries():                                  # (only real entries: padding must stay zero)
             net.live[vn.slot, e.offset:e.offset + e.numel] += 0.05 * (vn.gid + 1) * torch.randn(e.numel, device=net.device)
+            if e.name.endswith("running_var"):                       # honest running variances stay positive, as after real training
+                net.live[vn.slot, e.offset:e.offset + e.numel] = net.live[vn.slot, e.offset:e.offset + e.numel].abs() + 0.5
         if L.Pi:
             net.ints[vn.slot] = torch.arange(L.Pi, device=net.device) + 3 * vn.gid
     own = {vn.gid: {k: v.detach().cpu().clone() for k, v in L.row_views(net.live[vn.slot], net.ints[vn.slot]).items()} for vn in net.nodes}
@@ -132,6 +134,21 @@ def test_fullmesh_rank_sum_fedavg_matches_cpu_oracle(attack):
         finally:
             net.close()
     _assert_states_close(outs[0], outs[1])
+
+
+def test_ubar_rejects_nan_scoring_candidates_like_reference():
+    """A directed-deviation attacker (λ = −5) also flips the sign of the BatchNorm running variance, so its model evaluates to NaN
+    in the reference and UBAR's stage 2 rejects it (NaN ≤ own is false).  The fused scoring tape must propagate that NaN (ReLU /
+    max-pool written NaN-preserving), not launder it into a finite loss."""
+    cfg = _cfg("ubar", {"rho": 0.6, "alpha": 0.5}, n=24, topo={"type": "k-regular", "num_nodes": 24, "k": 4},
+               attack={"enabled": True, "type": "directed_deviation", "percentage": 0.3, "params": {"lambda_param": -5.0}}, model=HAR, data=HAR_DATA,
+               b200={"grouped_mlp": False})
+    net, adapter, mf = _build(cfg)
+    try:
+        got, want, own, pub = _oracle_round(net, cfg, adapter, mf)
+        _assert_states_close(got, want)
+    finally:
+        net.close()
 
 
 def test_fused_evidential_trust_matches_cpu_oracle():
