@@ -128,6 +128,8 @@ class B200Config(BaseModel):
         default="auto", description="train all nodes of a GPU with the fused tcgen05 program (parallel/fused_trainer.py: grouped implicit-GEMM "
                                     "conv / linear kernels with the SGD step in the wgrad epilogue, one CUDA graph per round); auto = whenever the "
                                     "model family, loss and layout are supported, otherwise the per-node autograd graphs")
+    score_tma: bool = Field(default=True, description="foreign-weight scoring (UBAR / EvidentialTrust / DMTT): feed the candidates' weights by TMA from "
+                            "their (peer-mapped) arenas, one launch per source GPU; false = cp.async gather through per-group row pointers")
     fullmesh_rank_sum: bool = Field(default=True, description="fully connected FedAvg: exchange one per-rank sum row (publish_sum → fedavg_fullmesh) "
                                     "instead of every node's row; false = the general edge-list gather")
     fused_eval_rows: int = Field(default=256, description="fused evaluation: samples per node and launch (nodes are sorted by shard size, so a "

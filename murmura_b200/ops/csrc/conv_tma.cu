@@ -41,6 +41,7 @@ struct alignas(64) ConvTmaParams {
     int nB;                         // images per node
     int PK, bh, bb, bpi;            // W: pixels per k-block = RW·bh·bb; k-blocks per image when bb == 1
     int prefill;                    // W: zero the stages before the first load (PK < 32) / write the all-ones bias atom
+    int g_off;                      // first group of this launch (scoring launches one group range per source GPU)
     TapClass cls[4];
 };
 
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(kCtThreads) conv_tma_kernel(const __grid_const
 
     pdl_launch_dependents();                    // the next kernel's prologue may overlap this one (it blocks in pdl_wait)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - g * p.splitk;
+    const int gl = (int)blockIdx.z / p.splitk, split = (int)blockIdx.z - gl * p.splitk;
+    const int g = gl + P.g_off;
     const int n0 = (int)blockIdx.y * BN;
     const int kb_begin = split * p.kb_per_split;
     const int ci = MODE == kModeW ? 0 : (int)blockIdx.x / P.mt_per_cls;             // tap class of this CTA (F / D)
@@ -296,6 +298,7 @@ int64_t conv_tma(py::dict d) {
         }
         TORCH_CHECK(P.ncls == 1 || P.g.splitk == 1, "conv_tma: class launches do not split K");
     }
+    P.g_off = dget<int>(d, "g_off", 0);
     P.PK = dget<int>(d, "PK", 32); P.bh = dget<int>(d, "bh", 1); P.bb = dget<int>(d, "bb", 1); P.bpi = dget<int>(d, "bpi", 1);
     const mb::ConvGemmParams& p = P.g;
     TORCH_CHECK(p.row_tab == nullptr, "conv_tma: per-group row tables are not supported (use conv_gemm)");

@@ -1176,6 +1176,45 @@ class B200Network:
         if st is None or st["fe"] is None:
             return False
         fe, G = st["fe"], len(jobs)
+        # group the jobs by the GPU that holds the candidate row: the TMA weight maps are per source arena (local or peer-mapped)
+        ar, plane_bytes = self.arena, 3 * self.S * self.layout.stride * 4
+        bases = [ar.base_ptr(r) for r in range(self.world)]
+
+        def locate(addr: int) -> Tuple[int, int]:
+            for r, b in enumerate(bases):
+                if 0 <= addr - b < plane_bytes:
+                    return r, (addr - b) // (self.layout.stride * 4)
+            raise RuntimeError("candidate row outside every arena")
+
+        located = [locate(int(j[2])) for j in jobs]
+        remote = sorted({loc for loc in located if loc[0] != self.rank})
+        if remote and self.opt.score_tma:
+            # candidates that live on peer GPUs are pulled over NVLink ONCE per round into a local mirror (every destination of
+            # this GPU that scores the same candidate, and every M tile of its GEMMs, then reads local HBM / L2)
+            self._mirror_cap = max(self.N - self.V, len(remote), 1)
+            mirror = self._buf(("score_mirror",), (self._mirror_cap, self.layout.stride))
+            if getattr(self, "_mirror_epoch", None) != self.epoch:       # UBAR and DMTT score the same published rows: copy once
+                self._mirror_epoch, self._mirror_where = self.epoch, {}
+            where = self._mirror_where
+            for loc in remote:
+                if loc not in where:
+                    r, ps = loc
+                    where[loc] = len(where)
+                    mirror[where[loc]].copy_(ar._view(r, ps * self.layout.stride * 4, [self.layout.stride], torch.float32), non_blocking=True)
+            mbase = mirror.data_ptr()
+            bases = bases + [mbase]
+            jobs = [(j[0], j[1], mbase + where[loc] * self.layout.stride * 4) if loc in where else j for j, loc in zip(jobs, located)]
+            located = [(self.world, where[loc]) if loc in where else loc for loc in located]
+        order = sorted(range(G), key=lambda i: (located[i][0], i))
+        jobs = [jobs[i] for i in order]
+        located = [located[i] for i in order]
+        parts, g0 = [], 0
+        for g in range(1, G + 1):
+            if g == G or located[g][0] != located[g0][0]:
+                src = located[g0][0]
+                parts.append((bases[src], 3 * self.S if src < self.world else self._mirror_cap, g0, g)); g0 = g
+        fe.score_parts = parts if (ar.off_live == 0 and self.opt.score_tma) else None
+        fe.wslot[:G] = torch.tensor([ps for _, ps in located], dtype=torch.int32, device=self.device)
         valid = []
         for vi, idx in samples.items():
             k = int(idx.numel())

@@ -87,6 +87,27 @@ class CudaBackend:
         self.launches += 1
         if warena is not None:
             row_tab = None                               # the packing kernel already resolved foreign rows
+        parts = getattr(tr, "score_parts", None) if row_tab is not None else None
+        if parts and geom is not None and getattr(tr, "use_tma", True):
+            # foreign-weight scoring on the TMA path: one launch per source GPU, weight maps over that GPU's (peer-mapped) arena
+            # [live | pub 0 | pub 1] planes, ``wslot[g]`` = plane·S + slot of group g's candidate row
+            maps = []
+            for base, slots, g0, g1 in parts:
+                key = (geom, plan["mode"], X.ptr(), Y.ptr(), plan["w_off"], int(base), int(slots))
+                if key not in self._tma:
+                    from murmura_b200.ops.conv_launch import encode_tma
+                    self._tma[key] = encode_tma(self.ext, plan["mode"], geom, x_ptr=X.ptr(), x_gs=X.gs, y_ptr=Y.ptr(), y_gs=Y.gs,
+                                                w_ptr=int(base) + plan["w_off"] * 4, arena_stride=int(tr.stride), slots=int(slots),
+                                                groups=int(X.t.shape[0]))
+                maps.append(self._tma[key])
+            if all(m is not None for m in maps):
+                for (base, slots, g0, g1), extra in zip(parts, maps):
+                    dd = dict(d); dd.update(extra)
+                    dd.update(G=int(g1 - g0), g_off=int(g0), arena=int(base), arena_gs=int(tr.stride), gmap=tr.wslot.data_ptr())
+                    self.ext.conv_tma(dd)
+                    self.tma_launches += 1
+                self.launches += len(parts) - 1
+                return
         if geom is not None and row_tab is None and getattr(tr, "use_tma", True):
             key = (geom, plan["mode"], X.ptr(), Y.ptr(), plan["w_off"], arena.data_ptr())
             if key not in self._tma:
@@ -953,6 +974,7 @@ class FusedForward:
         self.logits = self.xb = None
         self.npix = self.Csrc = self.Cdst = 0
         self.row_tab: Optional[torch.Tensor] = None
+        self.score_parts = None                         # [(arena base of a source GPU, slots, g0, g1)]: scoring on the TMA path
         try:
             self.supported = build_program(self, model, self.eb, sample_shape, training=False)
         except (_Unsupported, AssertionError) as exc:
@@ -969,6 +991,7 @@ class FusedForward:
             for op in self.pool_ops:
                 op.idx = torch.zeros(self.Gmax, op.B * op.OH * op.OW * op.C, dtype=torch.uint8, device=dev)
         self.gmap = torch.arange(self.Gmax, dtype=torch.int32, device=dev)
+        self.wslot = torch.zeros(self.Gmax, dtype=torch.int32, device=dev)
         self.yb = torch.zeros(self.Gmax, self.eb, dtype=torch.int64, device=dev)
         self.stats = torch.zeros(self.Gmax, 8, device=dev)
         self.wpack = torch.zeros(self.Gmax, wpack_row_floats(self.first), device=dev)
