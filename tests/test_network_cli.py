@@ -271,3 +271,32 @@ def test_public_api_parity_with_reference_package():
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "api_parity.py")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "## Missing (0)" in out.stdout, out.stdout[-3000:]
+
+
+def test_paper_figures_from_suite_results(tmp_path):
+    """The six paper figures (reference experiments/paper/generate_figures.py:109-513) from a run_suite results file."""
+    import importlib.util
+    import xml.dom.minidom
+    spec = importlib.util.spec_from_file_location("paper_figures", os.path.join(ROOT, "experiments", "paper_figures.py"))
+    pf = importlib.util.module_from_spec(spec); spec.loader.exec_module(pf)
+    index = {"heterogeneity": {}, "ablation": {}}
+    res = {}
+    for ds, base in (("uci_har", 0.80), ("pamap2", 0.70)):
+        for ai, algo in enumerate(pf.ALGORITHMS):
+            for al, bump in (("01", 0.0), ("05", 0.06), ("10", 0.10)):
+                key = f"{ds}__{algo}__a{al}"
+                index["heterogeneity"][f"{ds}/{algo}_alpha{al}"] = key + ".yaml"
+                res[key] = {"status": "ok", "final_accuracy": base + bump + 0.01 * ai, "final_std": 0.05, "convergence_round": 30 - 4 * ai, "rounds": []}
+        for p in ("accuracy_weight_03", "self_weight_05", "trust_threshold_01", "vacuity_threshold_05"):
+            key = f"{ds}__evidential_trust__abl_{p}"
+            index["ablation"][f"{ds}/{p}"] = key + ".yaml"
+            res[key] = {"status": "ok", "final_accuracy": 0.9, "final_std": 0.02, "convergence_round": 9, "rounds": []}
+    res["uci_har__ubar__a10"]["status"] = "error"                      # a failed run must not break the averages
+    data = pf.generate(res, index, str(tmp_path))
+    for name in ("fig1_noniid_robustness", "fig2_degradation", "fig3_personalization", "fig4_convergence", "fig5_ablation", "fig6_combined_summary"):
+        xml.dom.minidom.parse(str(tmp_path / f"{name}.svg"))
+    assert data["datasets"] == ["pamap2", "uci_har"]
+    assert abs(data["fig2_degradation"]["fedavg"] - 10.0) < 1e-6                     # (α=1.0) − (α=0.1) in points
+    assert data["fig4_convergence"]["evidential_trust"] == 14.0 and data["fig4_convergence"]["fedavg"] == 30.0
+    assert abs(data["fig1_noniid_robustness"]["fedavg"]["01"]["mean_acc"] - 75.0) < 1e-6
+    assert data["fig5_ablation"]["self_weight"]["runs"] == 2
