@@ -128,6 +128,10 @@ class B200Config(BaseModel):
         default="auto", description="train all nodes of a GPU with the fused tcgen05 program (parallel/fused_trainer.py: grouped implicit-GEMM "
                                     "conv / linear kernels with the SGD step in the wgrad epilogue, one CUDA graph per round); auto = whenever the "
                                     "model family, loss and layout are supported, otherwise the per-node autograd graphs")
+    seed_parity: bool = Field(default=False, description="draw model initialisation and the per-round shuffles from the SAME host RNG stream as the "
+                              "simulation backend / the reference (all N models built in node order from the caller's torch seed, one stock "
+                              "DataLoader-style permutation per node and epoch), so attack-free runs can be compared round by round; "
+                              "attack noise and dropout stay on the device Philox streams")
     score_tma: bool = Field(default=True, description="foreign-weight scoring (UBAR / EvidentialTrust / DMTT): feed the candidates' weights by TMA from "
                             "their (peer-mapped) arenas, one launch per source GPU; false = cp.async gather through per-group row pointers")
     fullmesh_rank_sum: bool = Field(default=True, description="fully connected FedAvg: exchange one per-rank sum row (publish_sum → fedavg_fullmesh) "

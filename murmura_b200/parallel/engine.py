@@ -244,7 +244,10 @@ class B200Network:
             sizes = [len(p) for p in dataset_adapter.get_client_partitions()]
             weights = [0.0 if i in self.compromised else float(max(1, n // max(1, min(bs_, max(2, n))))) for i, n in enumerate(sizes[: self.N])]
         self.placement = Placement(self.N, self.world, weights)
+        rng_state = torch.get_rng_state()
         probe = model_factory()
+        if self.opt.seed_parity:
+            torch.set_rng_state(rng_state)              # the layout probe must not advance the stream the node models are drawn from
         self.layout = StateLayout.from_model(probe, channels_last=bool(self.opt.channels_last))
         sketch_k = int(getattr(self.aggregator, "sketch_size", 0)) if self.family == "sketchguard" else 0
         auto = self.opt.transport == "auto"
@@ -282,9 +285,21 @@ class B200Network:
         self._host_shards: List[Tuple[torch.Tensor, torch.Tensor]] = []
         self.h2d_bytes_per_round = 0
         bs = config.training.batch_size
+        parity_models = {}
+        if self.opt.seed_parity:
+            # the simulation backend builds node 0 … N−1 in order from the caller's global torch stream (core/network.py from_config,
+            # reference murmura/core/network.py:262-300): replay exactly that on every rank, keep the local nodes' models
+            mine = set(self.local_gids)
+            for gid in range(self.N):
+                m = model_factory()
+                if gid in mine:
+                    parity_models[gid] = m
         for slot, gid in enumerate(self.local_gids):
-            torch.manual_seed(config.experiment.seed * 1000003 + gid)       # per-node init stream, rank-layout independent
-            model = model_factory().to(self.device)
+            if self.opt.seed_parity:
+                model = parity_models.pop(gid).to(self.device)
+            else:
+                torch.manual_seed(config.experiment.seed * 1000003 + gid)   # per-node init stream, rank-layout independent
+                model = model_factory().to(self.device)
             L.bind(model, self.live[slot], None, self.ints[slot] if L.Pi else None)
             X, y = dataset_adapter.client_tensors(gid)
             nhwc = bool(self.opt.channels_last) and X.dim() == 4
@@ -304,7 +319,9 @@ class B200Network:
                                           byzantine=gid in self.compromised, nhwc=nhwc,
                                           params=[p for p in model.parameters() if p.requires_grad]))
         del probe
-        torch.manual_seed(config.experiment.seed + 7919 * self.rank)
+        if not self.opt.seed_parity:                    # parity mode keeps consuming the caller's stream (shuffles below)
+            torch.manual_seed(config.experiment.seed + 7919 * self.rank)
+        self._shard_sizes = [len(p) for p in dataset_adapter.get_client_partitions()][: self.N] if self.opt.seed_parity else None
 
         # ---- attack parameters on the device (fused into publish) ------------------------------
         spec = self.attack.device_spec() if self.attack is not None and hasattr(self.attack, "device_spec") else None
@@ -593,8 +610,35 @@ class B200Network:
         for s in self.streams:
             ev = torch.cuda.Event(); ev.record(s); self.main.wait_event(ev)
 
+    def _parity_orders(self, epochs: int) -> Dict[int, torch.Tensor]:
+        """Seed-parity mode: this round's sample orders of the LOCAL nodes, drawn from the global host stream exactly as the
+        simulation backend's loaders draw them — nodes in id order, attackers skipped (they do not train), per epoch one int64
+        for the iterator's base seed, one int64 seeding a private generator, ``randperm(n)`` from it (``data/fast_loader.py``,
+        i.e. ``DataLoader(shuffle=True)``); every rank replays the whole sequence and keeps its own nodes."""
+        bs = int(self.cfg.training.batch_size)
+        by_gid = {vn.gid: vn for vn in self.nodes}
+        out: Dict[int, torch.Tensor] = {}
+        for gid in range(self.N):
+            if gid in self.compromised:
+                continue
+            n = int(self._shard_sizes[gid])
+            eb = min(bs, max(2, n))
+            nb = (n // eb) if n > eb else (1 if n >= 2 else 0)
+            rows = []
+            for _ in range(epochs):
+                torch.empty((), dtype=torch.int64).random_()
+                if n == 0:
+                    continue
+                g = torch.Generator()
+                g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+                rows.append(torch.randperm(n, generator=g)[: nb * min(eb, n)])
+            if gid in by_gid and rows and nb > 0:
+                out[gid] = torch.stack(rows)
+        return out
+
     def _local_training(self, epochs: int, lr: float) -> None:
         from murmura_b200.models.mlp import EvidentialLoss
+        self._round_orders = self._parity_orders(epochs) if self.opt.seed_parity else None
         self._fused_evidential = self.evidential and isinstance(self.criterion, EvidentialLoss)
         if isinstance(self.criterion, EvidentialLoss):
             self.lam_t.fill_(self.criterion.anneal(self.round_idx))
@@ -614,8 +658,11 @@ class B200Network:
                 continue
             with torch.cuda.stream(stream):
                 take = vn.nb * vn.eb
-                keys = torch.rand(epochs, vn.n, device=self.device)
-                vn.perm_buf.copy_(keys.argsort(dim=1)[:, :take].reshape(-1))
+                if self._round_orders is not None:
+                    vn.perm_buf.copy_(self._round_orders[vn.gid].reshape(-1).to(self.device, non_blocking=True))
+                else:
+                    keys = torch.rand(epochs, vn.n, device=self.device)
+                    vn.perm_buf.copy_(keys.argsort(dim=1)[:, :take].reshape(-1))
                 vn.step.zero_(); vn.loss_sum.zero_()
                 vn.model.train()
                 if vn.train_graph is not None:
@@ -677,7 +724,11 @@ class B200Network:
         for tr in trainers:
             tr.loss_acc.zero_()
             before = tr.be.launches
-            tr.run_round(epochs, lr)
+            perms = None
+            orders = getattr(self, "_round_orders", None)
+            if orders is not None:
+                perms = {vn.slot: orders[vn.gid] for vn in self.nodes if vn.gid in orders}
+            tr.run_round(epochs, lr, perms=perms)
             if tr.be.launches > before:                          # the round was (re)captured: remember its launch count
                 tr.launches_in_graph = (tr.be.launches - before) * tr.max_steps // (tr.max_steps + 1) if tr.max_steps else 0
             self.kernel_launches += getattr(tr, "launches_in_graph", 0)
@@ -1537,6 +1588,9 @@ class B200Network:
         return True
 
     def _evaluate(self) -> List[Dict[str, Any]]:
+        if self.opt.seed_parity:
+            for _ in range(self.N):                     # the simulation's N evaluation loaders each draw their iterator's base seed
+                torch.empty((), dtype=torch.int64).random_()
         if self._evaluate_fused():
             return self._collect_metrics()
         self._fork()

@@ -906,10 +906,20 @@ class FusedTrainer:
             per_epoch = self.steps[s] // max(epochs, 1) * self.eb
             self.perm[s, : epochs * per_epoch] = order[s, :, :per_epoch].reshape(-1)
 
-    def run_round(self, epochs: int, lr: float, use_graph: bool = True) -> None:
+    def set_permutations(self, perms: Dict[int, torch.Tensor]) -> None:
+        """Host-provided sample orders (seed-parity mode): ``perms[slot]`` = [epochs, nb·eb] indices of that node's shard."""
+        for s in self.order:
+            if s in perms:
+                flat = perms[s].reshape(-1).to(self.device, non_blocking=True)
+                self.perm[s, : flat.numel()] = flat
+
+    def run_round(self, epochs: int, lr: float, use_graph: bool = True, perms: Optional[Dict[int, torch.Tensor]] = None) -> None:
         if not self.supported or self.max_steps == 0:
             return
-        self.refresh_permutations(epochs)
+        if perms is not None:
+            self.set_permutations(perms)
+        else:
+            self.refresh_permutations(epochs)
         if self.be.name != "cuda" or not use_graph:
             return self.run_steps(lr)
         key = (epochs, lr)

@@ -225,6 +225,30 @@ def test_profile_mode_reports_phase_split_and_roofline_fraction():
         net.close()
 
 
+@pytest.mark.parametrize("algo,params", [("fedavg", {}), ("krum", {"num_compromised": 1}), ("balance", {"gamma": 0.5, "kappa": 1.0, "alpha": 0.5})])
+def test_seed_parity_mode_tracks_the_simulation_backend_round_by_round(algo, params):
+    """``b200.seed_parity``: model init and per-round shuffles come from the same host RNG stream as the simulation backend, so an
+    attack-free run is comparable round by round.  Autograd training path (same fp32 PyTorch kernels as the simulation): the
+    accuracy histories agree to 1e-3; fused tcgen05 path (TF32 operands): to a few samples."""
+    from murmura_b200.utils.seed import set_seed
+    data = {"adapter": "synthetic.mnist", "params": {"samples_per_node": 192, "partition_method": "dirichlet", "alpha": 0.5}}
+    topo = {"type": "k-regular", "num_nodes": 6, "k": 4}
+    hist = {}
+    for name, backend, b200 in (("sim", "simulation", {}), ("autograd", "b200", {"seed_parity": True, "fused_train": False, "krum_gram": "fp32"}),
+                                ("fused", "b200", {"seed_parity": True, "krum_gram": "fp32"})):
+        set_seed(11)
+        cfg = _cfg(algo, params, n=6, topo=topo, data=data, b200=b200, backend=backend, rounds=10)
+        net, _, _ = _build(cfg)
+        try:
+            hist[name] = net.train(rounds=10, local_epochs=2, lr=0.05)["mean_accuracy"]
+        finally:
+            if hasattr(net, "close"):
+                net.close()
+    assert hist["sim"][-1] > hist["sim"][1] and (algo != "fedavg" or hist["sim"][-1] > 0.8)
+    assert max(abs(a - b) for a, b in zip(hist["sim"], hist["autograd"])) <= 1e-3, (hist["sim"], hist["autograd"])
+    assert max(abs(a - b) for a, b in zip(hist["sim"], hist["fused"])) <= 2e-2, (hist["sim"], hist["fused"])
+
+
 def test_graphs_match_eager_and_simulation_statistically():
     accs = {}
     data = {"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}}
