@@ -128,6 +128,8 @@ class B200Config(BaseModel):
         default="auto", description="train all nodes of a GPU with the fused tcgen05 program (parallel/fused_trainer.py: grouped implicit-GEMM "
                                     "conv / linear kernels with the SGD step in the wgrad epilogue, one CUDA graph per round); auto = whenever the "
                                     "model family, loss and layout are supported, otherwise the per-node autograd graphs")
+    lazy_metrics: bool = Field(default=True, description="evaluated rounds write their metric table to a pinned host ring and `history` is filled "
+                               "lazily (no host synchronisation per round; verbose / profile runs stay round-by-round)")
     seed_parity: bool = Field(default=False, description="draw model initialisation and the per-round shuffles from the SAME host RNG stream as the "
                               "simulation backend / the reference (all N models built in node order from the caller's torch seed, one stock "
                               "DataLoader-style permutation per node and epoch), so attack-free runs can be compared round by round; "
@@ -136,6 +138,9 @@ class B200Config(BaseModel):
                             "their (peer-mapped) arenas, one launch per source GPU; false = cp.async gather through per-group row pointers")
     fullmesh_rank_sum: bool = Field(default=True, description="fully connected FedAvg: exchange one per-rank sum row (publish_sum → fedavg_fullmesh) "
                                     "instead of every node's row; false = the general edge-list gather")
+    fullmesh_two_shot: Union[bool, Literal["auto"]] = Field(default="auto", description="several GPUs: all-reduce the per-rank sum rows with the fused reduce-scatter + all-gather "
+                                    "kernel (each GPU reduces 1/G of the row and scatters it to every peer); false = every GPU reduces the whole row; "
+                                    "auto = two-shot from 4 GPUs (measured: one-shot peer loads win at 2 GPUs)")
     fused_eval_rows: int = Field(default=256, description="fused evaluation: samples per node and launch (nodes are sorted by shard size, so a "
                                  "chunk only runs the nodes that still have samples: no padding to the largest shard)")
     fused_side_stream: bool = Field(default=True, description="fused_train: weight-gradient launches on a parallel graph branch")

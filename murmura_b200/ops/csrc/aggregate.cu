@@ -263,12 +263,58 @@ __global__ void __launch_bounds__(kThreads) nvls_fedavg_kernel(NvlsArgs a) {
     }
 }
 
+// Two-shot all-reduce of the per-rank sum rows, written as ONE kernel over peer memory: this GPU reduces slice
+// [len·r/G, len·(r+1)/G) of the rsum rows of all ranks (one `multimem.ld_reduce` per 16 bytes when the arena is bound to an NVLS
+// multicast object — the switch adds; G peer loads otherwise) and immediately scatters the reduced values into the `total` row of
+// EVERY rank (`multimem.st`, or G peer stores), then raises its epoch flag (last block).  Per GPU and direction the fabric carries
+// one row instead of G−1 (peer loads) or G (every GPU asking the switch for the whole row).  Liveness is the frozen mask; with a
+// missing rank the kernel does nothing and `fedavg_fullmesh` falls back to the one-shot reduction over the ranks that arrived.
+__device__ __forceinline__ void multimem_st_v4(float* mc_addr, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct ReduceScatterArgs {
+    const float* const* peer_rsum; const float* mc_rsum; float* const* peer_tot; float* mc_tot;
+    int len4, G, my_rank; const uint32_t* timed_out;
+    uint32_t* const* peer_flags; uint32_t epoch; unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(kThreads) fullmesh_reduce_scatter_kernel(ReduceScatterArgs a) {
+    const uint32_t dead = a.timed_out ? *a.timed_out : 0u;
+    if (dead == 0u) {
+        const int lo = (int)((long long)a.len4 * a.my_rank / a.G), hi = (int)((long long)a.len4 * (a.my_rank + 1) / a.G);
+        for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+            float4 sum;
+            if (a.mc_rsum) sum = multimem_ld_reduce_add(a.mc_rsum + ((size_t)i << 2));
+            else {
+                sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < a.G; ++r) {
+                    const float4 x = ld_stream(reinterpret_cast<const float4*>(a.peer_rsum[r]) + i);
+                    sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+                }
+            }
+            if (a.mc_tot) multimem_st_v4(a.mc_tot + ((size_t)i << 2), sum);
+            else for (int r = 0; r < a.G; ++r) st_stream(reinterpret_cast<float4*>(a.peer_tot[r]) + i, sum);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            *a.ticket = 0;
+            for (int g = 0; g < a.G; ++g) st_release_sys(a.peer_flags[g] + a.my_rank, a.epoch);
+        }
+    }
+}
+
 // Full-mesh FedAvg on the per-rank sums: T = Σ_ranks rsum_r (one `multimem.ld_reduce` when the arena is bound to an NVLS
 // multicast object and every rank arrived, otherwise G−1 peer loads), then every local node gets T/N — a Byzantine
 // destination swaps its own (attacked) published term for its live row.  Bytes per GPU: one row in over the fabric,
 // V rows written: the minimal-byte schedule ("all destinations share the source set").  Liveness is the frozen mask.
 struct FullMeshArgs {
-    float* live; const float* pub_local; const float* const* peer_rsum; const float* mc_rsum;
+    float* live; const float* pub_local; const float* const* peer_rsum; const float* mc_rsum; const float* tot_local;
     size_t stride; int V, len4, G, N; const uint8_t* byz; const int* rank_nodes; const uint32_t* timed_out;
 };
 
@@ -278,9 +324,11 @@ __global__ void __launch_bounds__(kThreads) fedavg_fullmesh_kernel(FullMeshArgs 
     if (dead) for (int r = 0; r < a.G; ++r) if ((dead >> r) & 1u) n_alive -= a.rank_nodes[r];
     const float inv = 1.f / (float)max(n_alive, 1);
     const bool use_mc = a.mc_rsum != nullptr && dead == 0u && a.G > 1;
+    const bool use_tot = a.tot_local != nullptr && dead == 0u;           // two-shot: the reduced row is already in local HBM
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.len4; i += gridDim.x * blockDim.x) {
         float4 sum;
-        if (use_mc) sum = multimem_ld_reduce_add(a.mc_rsum + ((size_t)i << 2));
+        if (use_tot) sum = ld_stream(reinterpret_cast<const float4*>(a.tot_local) + i);
+        else if (use_mc) sum = multimem_ld_reduce_add(a.mc_rsum + ((size_t)i << 2));
         else {
             sum = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 0; r < a.G; ++r) {
@@ -980,14 +1028,31 @@ void publish_sum(Tensor live, int64_t pub_ptr, int64_t rsum_ptr, int64_t stride,
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+void fullmesh_reduce_scatter(Tensor anchor, int64_t peer_rsum_tbl, int64_t mc_rsum_ptr, int64_t peer_tot_tbl, int64_t mc_tot_ptr, int64_t len,
+                             int64_t G, int64_t my_rank, int64_t timed_out_ptr, int64_t peer_flags_ptr, int64_t epoch, Tensor ticket) {
+    c10::cuda::CUDAGuard guard(anchor.device());
+    TORCH_CHECK(G >= 2 && peer_flags_ptr != 0, "fullmesh_reduce_scatter needs >= 2 ranks");
+    mb::ReduceScatterArgs a;
+    a.peer_rsum = reinterpret_cast<const float* const*>(peer_rsum_tbl); a.mc_rsum = reinterpret_cast<const float*>(mc_rsum_ptr);
+    a.peer_tot = reinterpret_cast<float* const*>(peer_tot_tbl); a.mc_tot = reinterpret_cast<float*>(mc_tot_ptr);
+    a.len4 = (int)(len / 4); a.G = (int)G; a.my_rank = (int)my_rank; a.timed_out = reinterpret_cast<const uint32_t*>(timed_out_ptr);
+    a.peer_flags = reinterpret_cast<uint32_t* const*>(peer_flags_ptr); a.epoch = (uint32_t)epoch;
+    a.ticket = reinterpret_cast<unsigned int*>(ticket.data_ptr<int>());
+    const int slice4 = (a.len4 + a.G - 1) / a.G;
+    const int grid = std::max(1, std::min(148 * 4, (slice4 + mb::kThreads - 1) / mb::kThreads));
+    mb::fullmesh_reduce_scatter_kernel<<<grid, mb::kThreads, 0, cur_stream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
 void fedavg_fullmesh(Tensor live, int64_t pub_local_ptr, int64_t peer_rsum_tbl, int64_t mc_rsum_ptr, int64_t stride, int64_t V,
-                     int64_t len, int64_t N, int64_t G, Tensor byz, Tensor rank_nodes, int64_t timed_out_ptr) {
+                     int64_t len, int64_t N, int64_t G, Tensor byz, Tensor rank_nodes, int64_t timed_out_ptr, int64_t tot_local_ptr) {
     if (V == 0) return;
     c10::cuda::CUDAGuard guard(live.device());
     TORCH_CHECK(rank_nodes.dtype() == torch::kInt32 && rank_nodes.numel() >= G && byz.numel() >= V);
     mb::FullMeshArgs a;
     a.live = live.data_ptr<float>(); a.pub_local = reinterpret_cast<const float*>(pub_local_ptr);
     a.peer_rsum = reinterpret_cast<const float* const*>(peer_rsum_tbl); a.mc_rsum = reinterpret_cast<const float*>(mc_rsum_ptr);
+    a.tot_local = reinterpret_cast<const float*>(tot_local_ptr);
     a.stride = (size_t)stride; a.V = (int)V; a.len4 = (int)(len / 4); a.G = (int)G; a.N = (int)N;
     a.byz = byz.data_ptr<uint8_t>(); a.rank_nodes = rank_nodes.data_ptr<int>();
     a.timed_out = reinterpret_cast<const uint32_t*>(timed_out_ptr);

@@ -18,7 +18,9 @@ void publish_sum(Tensor live, int64_t pub_ptr, int64_t rsum_ptr, int64_t stride,
                  c10::optional<Tensor> ints, Tensor scale, Tensor noise_std, Tensor node_gid, int64_t seed, int64_t round,
                  int64_t peer_flags_ptr, int64_t G, int64_t my_rank, int64_t epoch, Tensor ticket);
 void fedavg_fullmesh(Tensor live, int64_t pub_local_ptr, int64_t peer_rsum_tbl, int64_t mc_rsum_ptr, int64_t stride, int64_t V,
-                     int64_t len, int64_t N, int64_t G, Tensor byz, Tensor rank_nodes, int64_t timed_out_ptr);
+                     int64_t len, int64_t N, int64_t G, Tensor byz, Tensor rank_nodes, int64_t timed_out_ptr, int64_t tot_local_ptr);
+void fullmesh_reduce_scatter(Tensor anchor, int64_t peer_rsum_tbl, int64_t mc_rsum_ptr, int64_t peer_tot_tbl, int64_t mc_tot_ptr, int64_t len,
+                             int64_t G, int64_t my_rank, int64_t timed_out_ptr, int64_t peer_flags_ptr, int64_t epoch, Tensor ticket);
 void nvls_fedavg(Tensor live, int64_t pub_local_ptr, int64_t mc_pub_ptr, int64_t stride, int64_t V, int64_t S, int64_t len,
                  int64_t N, Tensor byz, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
 void wait_epoch(Tensor anchor, int64_t flags_ptr, int64_t G, int64_t epoch, double timeout_ms, int64_t timed_out_ptr);
@@ -107,6 +109,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("wait_epoch", &wait_epoch);
     m.def("nvls_fedavg", &nvls_fedavg);
     m.def("publish_sum", &publish_sum, "publish + per-rank column sum of the published rows (full-mesh FedAvg)");
+    m.def("fullmesh_reduce_scatter", &fullmesh_reduce_scatter, "two-shot all-reduce of the per-rank sum rows over peer / multicast memory (one fused kernel)");
     m.def("fedavg_fullmesh", &fedavg_fullmesh, "full-mesh FedAvg from the per-rank sums (NVLS multimem.ld_reduce or peer loads)");
     m.def("edge_distances", &edge_distances);
     m.def("pairwise_distances", &pairwise_distances);

@@ -209,7 +209,8 @@ class SymmetricArena:
         self.off_sketch_sc = self.off_sketch_q + q_bytes
         sc_bytes = _ceil(2 * S * (self.Kpad // 32 if self.Kpad else 0), 256)
         self.off_rsum = _ceil(self.off_sketch_sc + sc_bytes, 256)     # per-rank column sums of the published rows, one per parity
-        self.off_ctrl = _ceil(self.off_rsum + 2 * stride * 4, 4096)
+        self.off_tot = _ceil(self.off_rsum + 2 * stride * 4, 256)      # all-reduced sum row (two-shot full-mesh FedAvg), one per parity
+        self.off_ctrl = _ceil(self.off_tot + 2 * stride * 4, 4096)
         total = self.off_ctrl + self.CTRL_BYTES
         index = device.index if device.index is not None else torch.cuda.current_device()
         self.backend = backend if self.world > 1 else "ipc"
@@ -251,6 +252,7 @@ class SymmetricArena:
         self.rsum = self._view(rank, self.off_rsum, [2, stride], torch.float32)
         self.rsum.zero_()
         self.tbl_rsum = [self._ptr_table(self.off_rsum + q * stride * 4) for q in (0, 1)]
+        self.tbl_tot = [self._ptr_table(self.off_tot + q * stride * 4) for q in (0, 1)]
 
     def _view(self, rank: int, byte_offset: int, sizes: List[int], dtype: torch.dtype) -> torch.Tensor:
         if self._arena is not None:
@@ -274,6 +276,12 @@ class SymmetricArena:
 
     def rsum_ptr(self, parity: int) -> int:
         return self._bases[self.rank] + self.off_rsum + parity * self.layout.stride * 4
+
+    def tot_ptr(self, parity: int) -> int:
+        return self._bases[self.rank] + self.off_tot + parity * self.layout.stride * 4
+
+    def mc_tot_ptr(self, parity: int) -> int:
+        return self.mc_base + self.off_tot + parity * self.layout.stride * 4 if self.mc_base else 0
 
     def mc_rsum_ptr(self, parity: int) -> int:
         return self.mc_base + self.off_rsum + parity * self.layout.stride * 4 if self.mc_base else 0

@@ -28,7 +28,7 @@ import math
 import os
 from contextlib import nullcontext
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -255,7 +255,9 @@ class B200Network:
             # full-mesh FedAvg over several GPUs: every node computes the same sum → let the NVSwitch add the ranks' copies
             # (each GPU ingests S·P instead of (N − V)·P bytes); everything else reads neighbour rows in-kernel over P2P
             full = all(len(set(self.topology.neighbors[i]) - {i}) == self.N - 1 for i in range(self.N))
-            nvls = self.world > 1 and self.family == "fedavg" and full and self.mobility is None and not self.opt.fault_drop_edges
+            # (measured at 2 GPUs: one-shot peer loads of the rank-sum rows beat the multicast path, 0.09 vs 0.15 ms; the switch pays off
+            # once G − 1 peer rows would have to cross the links)
+            nvls = self.world >= 4 and self.family == "fedavg" and full and self.mobility is None and not self.opt.fault_drop_edges
             self.opt.transport = "nvls" if nvls else "p2p"
         try:
             self.arena = SymmetricArena(self.layout, self.placement, self.rank, self.device, sketch_size=sketch_k,
@@ -903,6 +905,10 @@ class B200Network:
         self._stat_log.append(et["stats"][: self.V].clone())
 
     # ---- FedAvg ------------------------------------------------------------------------------
+    def _two_shot(self) -> bool:
+        v = self.opt.fullmesh_two_shot
+        return self.world >= 4 if v == "auto" else (bool(v) and self.world > 1)
+
     def _fullmesh_fedavg(self, et) -> bool:
         """True when every node averages the SAME set (fully connected FedAvg, no dropped edges, device-side attack): the
         round then moves one per-rank sum row instead of every node's row (``publish_sum`` → ``fedavg_fullmesh``)."""
@@ -924,9 +930,21 @@ class B200Network:
                 self._rank_nodes = torch.tensor([int(c) for c in self.placement.counts] + [0] * 16, dtype=torch.int32, device=self.device)[: max(self.world, 1)].contiguous()
             L = self.layout
             use_mc = self.opt.transport == "nvls" and self.world > 1 and self.arena.mc_base
+            tot = 0
+            if self._two_shot():
+                # reduce-scatter + all-gather of the rank sums in one kernel over peer / multicast memory, second epoch flag, then the
+                # apply kernel reads the reduced row from LOCAL memory
+                self.epoch += 1
+                self.ext.fullmesh_reduce_scatter(self.live, self.arena.tbl_rsum[parity].data_ptr(), self.arena.mc_rsum_ptr(parity) if use_mc else 0,
+                                                 self.arena.tbl_tot[parity].data_ptr(), self.arena.mc_tot_ptr(parity) if use_mc else 0,
+                                                 L.Pf_pad, self.world, self.rank, self._sync_args()[4], self.arena.tbl_flags.data_ptr(),
+                                                 self.epoch, self.ticket)
+                self.kernel_launches += 1
+                self._freeze_liveness()
+                tot = self.arena.tot_ptr(parity)
             self.ext.fedavg_fullmesh(self.live, self.arena.pub_plane_ptr(parity), self.arena.tbl_rsum[parity].data_ptr(),
                                      self.arena.mc_rsum_ptr(parity) if use_mc else 0, L.stride, self.V, L.Pf_pad, self.N, self.world,
-                                     et["byz"], self._rank_nodes, self._sync_args()[4])
+                                     et["byz"], self._rank_nodes, self._sync_args()[4], tot)
             self.kernel_launches += 1
             return                                            # int buffers keep own under FedAvg: nothing to blend
         if (self.opt.transport == "nvls" and self.world > 1 and et["full_mesh"] and self.arena.mc_base
@@ -1120,6 +1138,25 @@ class B200Network:
             t = self._mlp_bufs[key] = torch.zeros(*shape, dtype=dtype, device=self.device)
         return t
 
+    def _ints(self, values: Sequence[int], dtype=torch.int64) -> torch.Tensor:
+        """Device copy of a small host integer list WITHOUT a host synchronisation.  ``torch.tensor(list, device=cuda)`` is a
+        pageable H2D copy that blocks the host until the stream has drained (≈ 0.5 ms each behind a training phase — most of a
+        round for the small models).  Lists repeat round after round on static topologies, so the copies are cached by content;
+        misses go through a fresh pinned buffer with a non-blocking copy."""
+        key = (dtype, tuple(values))
+        cache = self.__dict__.setdefault("_ints_cache", {})
+        t = cache.get(key)
+        if t is None:
+            if len(cache) >= 256:                            # dynamic topologies: bounded, oldest entries go first
+                for k in list(cache)[:64]:
+                    del cache[k]
+            host = torch.tensor(list(values) or [0], dtype=dtype).pin_memory()
+            t = cache[key] = host.to(self.device, non_blocking=True)
+            self.__dict__.setdefault("_ints_pinned", []).append(host)     # keep the staging buffers alive until their copies ran
+            if len(self._ints_pinned) > 512:
+                del self._ints_pinned[:256]
+        return t
+
     def _grouped_mlp_scores(self, jobs: List[Tuple[int, int, int]], inputs: Dict[int, Tuple[torch.Tensor, torch.Tensor]],
                             kind: str, stats: torch.Tensor) -> None:
         """``jobs`` = (stats_row, destination vi, weight-row address).  One launch per layer for ALL jobs."""
@@ -1157,7 +1194,7 @@ class B200Network:
         tmp.zero_()
         self.ext.grouped_eval(torch.from_numpy(ev).to(self.device, non_blocking=True), G, max_m, plan[-1]["N"], plan[-1]["N"],
                               kind == "dirichlet", tmp)
-        stats.index_copy_(0, torch.tensor([j[0] for j in jobs], device=self.device), tmp)
+        stats.index_copy_(0, self._ints([j[0] for j in jobs]), tmp)
         self.kernel_launches += len(plan) + 1
 
     def _flat_inputs(self, vn: VirtualNode, idx: Optional[torch.Tensor], tag: str) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -1265,7 +1302,7 @@ class B200Network:
                 src = located[g0][0]
                 parts.append((bases[src], 3 * self.S if src < self.world else self._mirror_cap, g0, g)); g0 = g
         fe.score_parts = parts if (ar.off_live == 0 and self.opt.score_tma) else None
-        fe.wslot[:G] = torch.tensor([ps for _, ps in located], dtype=torch.int32, device=self.device)
+        fe.wslot[:G] = self._ints([ps for _, ps in located], torch.int32)
         valid = []
         for vi, idx in samples.items():
             k = int(idx.numel())
@@ -1274,14 +1311,14 @@ class B200Network:
                 st["perm"][vi, k:] = idx[-1]
         for _, vi, _ in jobs:
             valid.append(int(samples[vi].numel()))
-        fe.gmap[:G] = torch.tensor([vi for _, vi, _ in jobs], dtype=torch.int32, device=self.device)
-        st["row_tab"][:G] = torch.tensor([a for _, _, a in jobs], dtype=torch.int64, device=self.device)
+        fe.gmap[:G] = self._ints([vi for _, vi, _ in jobs], torch.int32)
+        st["row_tab"][:G] = self._ints([a for _, _, a in jobs])
         fe.load(G, st["x_tab"], st["y_tab"], st["perm"], 0)
         fe.forward(G)
         tmp = st["stats"][:G]
         tmp.zero_()
         fe.metrics(G, fe.eval_descriptors(valid), tmp, dirichlet=(kind == "dirichlet"))
-        stats.index_copy_(0, torch.tensor([j[0] for j in jobs], device=self.device), tmp)
+        stats.index_copy_(0, self._ints([j[0] for j in jobs]), tmp)
         self.kernel_launches += len(fe.ops) + 2
         return True
 
@@ -1323,7 +1360,7 @@ class B200Network:
             mean_loss = stats[:, 0] / stats[:, 2].clamp_min(1.0)
             loss.copy_(mean_loss[: loss.numel()])
             if self.V:
-                own_loss[: self.V] = mean_loss[torch.tensor(rows[: self.V], device=self.device)]
+                own_loss[: self.V] = mean_loss[self._ints(rows[: self.V])]
             self.ext.ubar_stage2(*self._et_args(et), cand, rank_t, loss, own_loss, a.alpha, True)
             self.kernel_launches += 1
             self._log_stats(et)
@@ -1354,7 +1391,7 @@ class B200Network:
         self._join()
         mean_loss = stats[:, 0] / stats[:, 2].clamp_min(1.0)
         loss.copy_(mean_loss[: loss.numel()])
-        own_loss[: self.V] = mean_loss[torch.tensor(rows[: self.V], device=self.device)] if self.V else own_loss[: self.V]
+        own_loss[: self.V] = mean_loss[self._ints(rows[: self.V])] if self.V else own_loss[: self.V]
         self.ext.ubar_stage2(*self._et_args(et), cand, rank_t, loss, own_loss, a.alpha, True)
         self.kernel_launches += 1
         self._log_stats(et)
@@ -1495,8 +1532,16 @@ class B200Network:
             # publish_sum: V rows read, V + 1 written; fedavg_fullmesh: own sum row read, V rows written; fabric: one row per peer
             # (or ONE multicast row when the NVSwitch reduces)
             nvls = self.opt.transport == "nvls" and self.arena.mc_base
-            self.timers["hbm_bytes"] = self.timers.get("hbm_bytes", 0.0) + row * (3 * self.V + 2)
-            self.timers["nvlink_bytes"] = self.timers.get("nvlink_bytes", 0.0) + row * (0 if self.world == 1 else (1 if nvls else self.world - 1))
+            G = self.world
+            if self._two_shot():
+                # inbound per GPU: the (G−1)/G remote parts of its own slice (or the switch-reduced slice) + the G−1 slices the peers scatter
+                link = row * ((1.0 / G + (G - 1.0) / G) if nvls else 2.0 * (G - 1.0) / G)
+                hbm = row * (3 * self.V + 4)
+            else:
+                link = row * (0 if G == 1 else (1 if nvls else G - 1))
+                hbm = row * (3 * self.V + 2)
+            self.timers["hbm_bytes"] = self.timers.get("hbm_bytes", 0.0) + hbm
+            self.timers["nvlink_bytes"] = self.timers.get("nvlink_bytes", 0.0) + link
             return
         passes = 1.0 + self._FILTER_ROW_PASSES.get(self.family, 0.0)
         extra = self.V if self.family == "sketchguard" else (self.N / max(self.world, 1) if self.family == "krum" else 0.0)
@@ -1587,12 +1632,12 @@ class B200Network:
         self.kernel_launches += st["launches"]
         return True
 
-    def _evaluate(self) -> List[Dict[str, Any]]:
+    def _evaluate(self, enqueue_only: bool = False) -> Optional[List[Dict[str, Any]]]:
         if self.opt.seed_parity:
             for _ in range(self.N):                     # the simulation's N evaluation loaders each draw their iterator's base seed
                 torch.empty((), dtype=torch.int64).random_()
         if self._evaluate_fused():
-            return self._collect_metrics()
+            return None if enqueue_only else self._collect_metrics()
         self._fork()
         for i in self.launch_order:
             vn = self.nodes[i]
@@ -1606,10 +1651,19 @@ class B200Network:
                     self._eval_node(vn)
                 self.kernel_launches += (vn.n + max(1, self.opt.eval_batch) - 1) // max(1, self.opt.eval_batch)
         self._join()
-        return self._collect_metrics()
+        return None if enqueue_only else self._collect_metrics()
 
-    def _collect_metrics(self) -> List[Dict[str, Any]]:
+    # ---- metrics ring: evaluated rounds leave their [N, 8] table in a pinned host ring; the host reads it LATER ----
+    _RING = 64
+
+    def _metrics_enqueue(self) -> Tuple[int, "torch.cuda.Event"]:
+        """Stream-ordered: gather every rank's metric rows and copy them (non-blocking) into the next ring slot.  No host sync —
+        the nodes' critical path never waits for the monitor (reference ``distributed/monitor.py:81-128`` is equally passive)."""
         S = self.placement.slots_per_rank
+        if not hasattr(self, "_ring"):
+            self._ring = torch.zeros(self._RING, S * self.world, _STAT_COLS).pin_memory()
+            self._ring_to = torch.zeros(self._RING, dtype=torch.int32).pin_memory()
+            self._ring_next = 0
         local = torch.zeros(S, _STAT_COLS, device=self.device)
         local[: self.V] = self.eval_stats[: self.V]
         if self.world > 1:
@@ -1617,17 +1671,25 @@ class B200Network:
             _dist().all_gather_into_tensor(full, local)
         else:
             full = local
-        self.metrics_host[: full.shape[0]].copy_(full, non_blocking=True)
+        slot = self._ring_next % self._RING
+        self._ring_next += 1
+        self._ring[slot].copy_(full, non_blocking=True)
         if self.world > 1 and hasattr(self, "_timeout_acc"):
-            self._timeout_host.copy_(self._timeout_acc, non_blocking=True)
+            self._ring_to[slot: slot + 1].copy_(self._timeout_acc, non_blocking=True)
             self._timeout_acc.zero_()
-        torch.cuda.current_stream().synchronize()          # the one host sync per evaluated round
-        if self.world > 1 and hasattr(self, "_timeout_host") and int(self._timeout_host[0]):
-            late = [r for r in range(self.world) if int(self._timeout_host[0]) >> r & 1]
-            self.timeout_events = getattr(self, "timeout_events", []) + [(self.round_idx + 1, late)]
-            print(f"[b200 rank {self.rank}] round {self.round_idx + 1}: rank(s) {late} did not publish within "
+        ev = torch.cuda.Event()
+        ev.record()
+        return slot, ev
+
+    def _metrics_from_slot(self, slot: int, round_no: int) -> List[Dict[str, Any]]:
+        S = self.placement.slots_per_rank
+        if self.world > 1 and int(self._ring_to[slot]):
+            mask = int(self._ring_to[slot]); self._ring_to[slot] = 0
+            late = [r for r in range(self.world) if mask >> r & 1]
+            self.timeout_events = getattr(self, "timeout_events", []) + [(round_no, late)]
+            print(f"[b200 rank {self.rank}] round {round_no}: rank(s) {late} did not publish within "
                   f"{self.opt.flag_timeout_ms:.0f} ms; their nodes were aggregated as missing neighbours")
-        host = self.metrics_host.numpy()
+        host = self._ring[slot].numpy()
         per_node = []
         for gid in range(self.N):
             r, s = int(self.placement.rank_of[gid]), int(self.placement.slot_of[gid])
@@ -1639,6 +1701,24 @@ class B200Network:
                 m.update(vacuity=float(row[3]) / total, entropy=float(row[4]) / total, strength=float(row[5]) / total)
             per_node.append(m)
         return per_node
+
+    def _collect_metrics(self) -> List[Dict[str, Any]]:
+        """Synchronous form (direct ``_evaluate()`` callers): enqueue, wait for that slot, decode."""
+        slot, ev = self._metrics_enqueue()
+        ev.synchronize()
+        return self._metrics_from_slot(slot, self.round_idx + 1)
+
+    def _drain_metrics(self, block: bool, verbose: bool = False) -> None:
+        """Move finished ring slots into ``history`` in round order; ``block`` waits for all of them (end of ``train``, a full
+        ring, verbose printing, checkpoints)."""
+        pend = self.__dict__.setdefault("_pending_metrics", [])
+        while pend:
+            round_no, slot, ev = pend[0]
+            if not block and not ev.query():
+                break
+            ev.synchronize()
+            record_round(self.history, round_no, self._metrics_from_slot(slot, round_no), self.compromised if self.attack else None, verbose)
+            pend.pop(0)
 
     def _capture_eval(self, vn: VirtualNode) -> None:
         side = self.capture_streams[self.stream_of[vn.slot]]
@@ -1740,7 +1820,7 @@ class B200Network:
         ev_i = [vi for vi in range(self.V) for _ in range(rows[vi] + 1, rows[vi + 1])]
         ee_i = [e for vi in range(self.V) for e in range(rows[vi] + 1, rows[vi + 1])]
         if ee_i:
-            vi_t = torch.tensor(ev_i, device=self.device); e_t = torch.tensor(ee_i, device=self.device)
+            vi_t = self._ints(ev_i); e_t = self._ints(ee_i)
             g_t = et["src_gid"].long().index_select(0, e_t)
             score[vi_t, g_t] = s_e.index_select(0, e_t); valid[vi_t, g_t] = 1; received[vi_t, g_t] = 1
         self.ext.dmtt_update(self.adj_dev, self.claims_dev, self.collab, received, score, valid, self.c_hat, self.t_alpha,
@@ -1791,8 +1871,13 @@ class B200Network:
             if prof:
                 ev[2].record(); nvtx.range_pop(); nvtx.range_push("evaluate")
             if (r + 1) % eval_every == 0:
-                per_node = self._evaluate()
-                record_round(self.history, r + 1, per_node, self.compromised if self.attack else None, verbose)
+                # evaluation is enqueued; its metric table lands in the pinned ring and is folded into ``history`` lazily, so the
+                # host keeps enqueueing the next round while the GPU is still busy (verbose runs print round by round: blocking)
+                self._evaluate(enqueue_only=True)
+                pend = self.__dict__.setdefault("_pending_metrics", [])
+                pend.append((r + 1, *self._metrics_enqueue()))
+                lazy = self.opt.lazy_metrics and not verbose and not prof
+                self._drain_metrics(block=not lazy or len(pend) >= self._RING - 2, verbose=verbose)
             if prof:
                 nvtx.range_pop(); nvtx.range_pop()
                 ev[3].record(); torch.cuda.synchronize()
@@ -1801,7 +1886,9 @@ class B200Network:
             self.timers["rounds"] += 1
             self.round_idx += 1
             if self.opt.checkpoint_every and self.round_idx % self.opt.checkpoint_every == 0:
+                self._drain_metrics(block=True)
                 self.save_checkpoint(os.path.join(self.opt.checkpoint_dir, f"round_{self.round_idx:05d}"))
+        self._drain_metrics(block=True)
         return self.history
 
     # =========================================================================================

@@ -899,7 +899,9 @@ class FusedTrainer:
         ns = [int(self.shards[s][1].shape[0]) for s in range(len(self.shards))]
         n_max = max(ns)
         keys = torch.rand(len(ns), epochs, n_max, device=self.device, generator=generator)
-        valid = torch.arange(n_max, device=self.device)[None, None, :] < torch.tensor(ns, device=self.device)[:, None, None]
+        if getattr(self, "_valid_mask", None) is None:      # shard sizes are fixed: build the mask once (a per-round host list → device
+            self._valid_mask = torch.arange(n_max, device=self.device)[None, None, :] < torch.tensor(ns, device=self.device)[:, None, None]
+        valid = self._valid_mask                            # copy would block the host until the stream drains)
         keys = torch.where(valid, keys, torch.full_like(keys, 2.0))
         order = keys.argsort(dim=2)                                   # [S, epochs, n_max], invalid indices last
         for s in self.order:
@@ -1018,8 +1020,18 @@ class FusedForward:
 
     def eval_descriptors(self, valid_rows: Sequence[int]) -> torch.Tensor:
         """Device table for :meth:`metrics`: (outputs, labels, #valid rows) of every group."""
-        host = [[self.logits.ptr() + g * self.logits.gs * 4, self.yb.data_ptr() + g * self.yb.shape[1] * 8, int(v)] for g, v in enumerate(valid_rows)]
-        return torch.tensor(host or [[0, 0, 0]], dtype=torch.int64, device=self.device)
+        key = tuple(int(v) for v in valid_rows)
+        cache = self.__dict__.setdefault("_desc_cache", {})
+        if key not in cache:                            # content-keyed: no per-round (host-synchronising) pageable upload
+            host = [[self.logits.ptr() + g * self.logits.gs * 4, self.yb.data_ptr() + g * self.yb.shape[1] * 8, v] for g, v in enumerate(key)]
+            t = torch.tensor(host or [[0, 0, 0]], dtype=torch.int64)
+            if self.device.type == "cuda":
+                t = t.pin_memory()
+                self.__dict__.setdefault("_desc_pinned", []).append(t)
+            if len(cache) > 128:
+                cache.clear()
+            cache[key] = t.to(self.device, non_blocking=True)
+        return cache[key]
 
     def metrics(self, G: int, desc: torch.Tensor, stats: Optional[torch.Tensor] = None, dirichlet: Optional[bool] = None) -> None:
         """Accumulate the per-group metric rows (zero ``stats`` first).  ``dirichlet=False`` forces softmax-CE on the raw outputs

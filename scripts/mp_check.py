@@ -145,6 +145,8 @@ def main():
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"fullmesh_rank_sum": False})                         # edge-list gather
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"transport": "nvls", "fullmesh_rank_sum": False})    # per-slot multimem
     check("fedavg", {}, n + 1, {"type": "fully", "num_nodes": n + 1}, b200={"transport": "nvls"})                        # uneven slots per rank
+    check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"fullmesh_two_shot": False})                         # one-shot rank sums (p2p)
+    check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"transport": "nvls", "fullmesh_two_shot": False})    # one-shot, multimem
     check("balance", {"gamma": 0.6, "alpha": 0.5}, n, kreg)
     check("krum", {"num_compromised": 1}, n, kreg, b200={"krum_gram": "fp32"})
     check("krum", {"num_compromised": 1}, n, kreg, b200={"krum_gram": "tcgen05"})

@@ -18,10 +18,10 @@ rank, world, _ = init_distributed()
 n = 8 if world <= 8 else world
 
 
-def build(transport, topo, gather="ldg", rank_sum=True):
+def build(transport, topo, gather="ldg", rank_sum=True, two_shot=True):
     cfg = Config(**{"experiment": {"name": "p2p", "rounds": 4, "seed": 1}, "topology": topo, "aggregation": {"algorithm": "fedavg"},
                     "training": {"batch_size": 16, "lr": 0.01}, "data": {"adapter": "synthetic.cifar10", "params": {"samples_per_node": 16, "partition_method": "iid"}},
-                    "model": {"factory": "models.resnet18"}, "backend": "b200", "b200": {"transport": transport, "placement": "contiguous", "cuda_graphs": False, "gather_impl": gather, "fullmesh_rank_sum": rank_sum}})
+                    "model": {"factory": "models.resnet18"}, "backend": "b200", "b200": {"transport": transport, "placement": "contiguous", "cuda_graphs": False, "gather_impl": gather, "fullmesh_rank_sum": rank_sum, "fullmesh_two_shot": two_shot}})
     ad = build_dataset_adapter(cfg); mf = build_model_factory(cfg)
     return Network.from_config(cfg, mf, ad, build_aggregator_factory(cfg, mf))
 
@@ -49,17 +49,26 @@ def timed(net, reps=12):
 
 
 out = []
-for transport, topo_name, gather, rank_sum in (("p2p", "fully", "ldg", True), ("nvls", "fully", "ldg", True), ("p2p", "fully", "ldg", False),
-                                              ("p2p", "fully", "tma", False), ("nvls", "fully", "ldg", False), ("p2p", "ring", "ldg", False),
-                                              ("p2p", "ring", "tma", False)):
+for transport, topo_name, gather, rank_sum, two_shot in (("p2p", "fully", "ldg", True, True), ("nvls", "fully", "ldg", True, True),
+                                                        ("p2p", "fully", "ldg", True, False), ("nvls", "fully", "ldg", True, False),
+                                                        ("p2p", "fully", "ldg", False, False), ("p2p", "fully", "tma", False, False),
+                                                        ("nvls", "fully", "ldg", False, False), ("p2p", "ring", "ldg", False, False),
+                                                        ("p2p", "ring", "tma", False, False)):
     topo = {"type": topo_name, "num_nodes": n}
-    net = build(transport, topo, gather, rank_sum)
+    net = build(transport, topo, gather, rank_sum, two_shot)
     ms = timed(net)
     L, pl = net.layout, net.placement
     remote = sum(1 for vn in net.nodes for j in net.topology.neighbors[vn.gid] if pl.rank_of[j] != net.rank)
     local = sum(1 for vn in net.nodes for j in net.topology.neighbors[vn.gid] if pl.rank_of[j] == net.rank) + len(net.nodes)
     row = L.Pf_pad * 4
-    if rank_sum and topo_name == "fully":
+    if rank_sum and two_shot and topo_name == "fully":
+        if transport == "nvls":
+            link_bytes = row * (1.0 / world + (world - 1.0) / world)
+            note = "two-shot on rank sums: multimem.ld_reduce of the own slice + multimem.st of it to every GPU"
+        else:
+            link_bytes = row * 2.0 * (world - 1.0) / world
+            note = "two-shot on rank sums: own slice from every peer + reduced slices scattered by peer stores"
+    elif rank_sum and topo_name == "fully":
         if transport == "nvls":
             link_bytes = row * (world - 1) / world
             note = "per-rank sum rows, multimem.ld_reduce: ONE reduced row per GPU"
@@ -72,7 +81,7 @@ for transport, topo_name, gather, rank_sum in (("p2p", "fully", "ldg", True), ("
     else:
         link_bytes = remote * row
         note = f"{remote} remote + {local} local row reads per GPU"
-    rec = {"kernel": f"fedavg exchange+aggregate ({transport}, {topo_name}, gather={gather}, rank_sum={rank_sum and topo_name == 'fully'})", "gpus": world, "nodes": n, "ms": round(ms, 4),
+    rec = {"kernel": f"fedavg exchange+aggregate ({transport}, {topo_name}, gather={gather}, rank_sum={rank_sum and topo_name == 'fully'}, two_shot={rank_sum and two_shot and topo_name == 'fully'})", "gpus": world, "nodes": n, "ms": round(ms, 4),
            "nvlink_GB_per_gpu": round(link_bytes / 1e9, 4), "nvlink_GBps": round(link_bytes / ms / 1e6, 1),
            "frac_of_measured_nvlink": round(link_bytes / ms / 1e6 / NVLINK_GBS, 3), "note": note}
     out.append(rec)
