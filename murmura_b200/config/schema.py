@@ -150,7 +150,10 @@ class B200Config(BaseModel):
                               "grouped tcgen05 forward (TF32) instead of per-candidate graph replays (fp32)")
     streams: int = Field(default=0, description="concurrent CUDA streams for virtual-node training (0 = auto: min(16, nodes on this GPU))")
     eval_batch: int = Field(default=1024, description="evaluation micro-batch (results are batch-size independent)")
-    flag_timeout_ms: float = Field(default=60000.0, description="device-side wait budget for a peer's publish flag; a rank that stays silent "
+    host_barrier_rounds: int = Field(default=3, description="rounds after (re)configuration in which the ranks meet on the host (key-value store, no GPU "
+                                     "work) between publishing and spinning on the peers' flags: while workspaces / CUDA graphs are still being "
+                                     "allocated, a cudaMalloc can block behind a peer GPU's spin-wait kernel")
+    flag_timeout_ms: float = Field(default=30000.0, description="device-side wait budget for a peer's publish flag; a rank that stays silent "
                                    "longer is treated as missing for the round (and reported): the reference's deadline-driven partial aggregation")
     fault_drop_edges: Dict[int, list] = Field(
         default_factory=dict, description="fault injection: {round: [[src, dst], ...]} edges to drop")

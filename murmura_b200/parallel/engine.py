@@ -244,6 +244,9 @@ class B200Network:
             sizes = [len(p) for p in dataset_adapter.get_client_partitions()]
             weights = [0.0 if i in self.compromised else float(max(1, n // max(1, min(bs_, max(2, n))))) for i, n in enumerate(sizes[: self.N])]
         self.placement = Placement(self.N, self.world, weights)
+        B200Network._NETS_BUILT += 1
+        self._net_id = B200Network._NETS_BUILT
+        self._barrier_until = int(self.opt.host_barrier_rounds)
         rng_state = torch.get_rng_state()
         probe = model_factory()
         if self.opt.seed_parity:
@@ -1103,10 +1106,36 @@ class B200Network:
             self.ext.wait_epoch(self.live, fp, G, ep, to, tp)
             self.kernel_launches += 1
 
+    _NETS_BUILT = 0                                     # construction order is identical on every rank: names the host barriers
+
+    def _host_barrier(self) -> None:
+        """CPU-only rendezvous through the process group's key-value store (no GPU work, no NCCL kernel).
+
+        Why: a spin-wait kernel on GPU A (``wait_epoch``, or any NCCL kernel) keeps A busy until GPU B publishes — and while A is
+        busy, a ``cudaMalloc`` on B can block, because with peer mappings enabled a new allocation has to be mapped on the peers too.
+        If B still has to allocate before its publish is enqueued (first rounds: workspaces, CUDA-graph capture), B waits for A and A
+        waits for B until the flag timeout fires and B's nodes are dropped for the round.  During the warm-up rounds every rank
+        therefore enqueues its publish FIRST, meets the others here on the host, and only then launches the wait: whatever a peer
+        still allocates afterwards, the flag this GPU spins on is already on its way."""
+        import time
+        from torch.distributed import distributed_c10d as c10d
+        try:
+            store = c10d._get_default_store()
+        except Exception:  # noqa: BLE001 - no store (single process): nothing to do
+            return
+        self._hb_count = getattr(self, "_hb_count", 0) + 1
+        key = f"murmura_b200/hb/{self._net_id}/{self._hb_count}"
+        store.add(key, 1)
+        deadline = time.time() + max(1.0, self.opt.flag_timeout_ms / 1000.0)
+        while int(store.add(key, 0)) < self.world and time.time() < deadline:
+            time.sleep(0.0002)
+
     def _freeze_liveness(self) -> None:
         """One wait on the epoch flags decides which peers arrived; every later kernel of the round consumes that mask."""
         if self.world == 1:
             return
+        if self.round_idx < self._barrier_until or getattr(self, "_warm_rounds", 0) > 0:
+            self._host_barrier()
         self._liveness_frozen = False
         self._host_wait_epoch()
         self._liveness_frozen = True
@@ -1853,6 +1882,10 @@ class B200Network:
     def train(self, rounds: int, local_epochs: int = 1, lr: float = 0.01, verbose: bool = False,
               eval_every: int = 1) -> Dict[str, List[Any]]:
         verbose = verbose and self.is_primary
+        seen = self.__dict__.setdefault("_train_keys", set())
+        if (local_epochs, lr, eval_every) not in seen:            # new graphs / workspaces get allocated in the next rounds
+            seen.add((local_epochs, lr, eval_every))
+            self._warm_rounds = max(getattr(self, "_warm_rounds", 0), int(self.opt.host_barrier_rounds))
         self._prepare_training(local_epochs, lr)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         total_rounds = self.round_idx + rounds
@@ -1884,6 +1917,7 @@ class B200Network:
                 self.timers["train_ms"] += ev[0].elapsed_time(ev[1]); self.timers["aggregate_ms"] += ev[1].elapsed_time(ev[2])
                 self.timers["eval_ms"] += ev[2].elapsed_time(ev[3])
             self.timers["rounds"] += 1
+            self._warm_rounds = max(0, getattr(self, "_warm_rounds", 0) - 1)
             self.round_idx += 1
             if self.opt.checkpoint_every and self.round_idx % self.opt.checkpoint_every == 0:
                 self._drain_metrics(block=True)

@@ -8,12 +8,16 @@ import torch
 from torch.profiler import ProfilerActivity, profile
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--config", type=int, default=2); ap.add_argument("--rounds", type=int, default=3); ap.add_argument("--out", default="")
+ap.add_argument("--config", default="2", help="BASELINE config index (2..5) or a YAML path"); ap.add_argument("--rounds", type=int, default=3); ap.add_argument("--out", default="")
 ap.add_argument("--top", type=int, default=30)
 ap.add_argument("--phase", default="round", choices=["round", "train", "aggregate", "eval"])
 args = ap.parse_args()
 import bench
-cfg = bench.load_bench_config(args.config)
+if str(args.config).isdigit():
+    cfg = bench.load_bench_config(int(args.config))
+else:
+    from murmura_b200.config import load_config
+    cfg = load_config(args.config); cfg.backend = "b200"
 net = bench.build_network(cfg, torch.device("cuda:0")) if hasattr(bench, "build_network") else None
 if net is None:
     from murmura_b200 import Network

@@ -102,7 +102,8 @@ def check(algo, params, n, topo, b200=None, attack=ATTACK, rounds=2, tol=5e-5):
 
 def train_check():
     """Short real training across ranks: accuracy must improve and histories agree on every rank."""
-    cfg = Config(**{"experiment": {"name": "mp-train", "rounds": 4, "seed": 5}, "topology": {"type": "ring", "num_nodes": 6},
+    nodes = max(6, dist.get_world_size())            # every rank hosts at least one node
+    cfg = Config(**{"experiment": {"name": "mp-train", "rounds": 4, "seed": 5}, "topology": {"type": "ring", "num_nodes": nodes},
                     "aggregation": {"algorithm": "fedavg"}, "training": {"batch_size": 32, "lr": 0.05},
                     "data": {"adapter": "synthetic.mnist", "params": {"samples_per_node": 128, "partition_method": "iid"}},
                     "model": {"factory": "models.mlp", "params": {"hidden_dims": [32]}}, "backend": "b200"})
@@ -114,7 +115,7 @@ def train_check():
     assert torch.equal(acc, ref), "ranks disagree on history"
     assert acc[-1] > acc[0] + 0.1, acc
     if dist.get_rank() == 0:
-        print("OK training ring6 fedavg acc", [round(float(a), 3) for a in acc], flush=True)
+        print(f"OK training ring{nodes} fedavg acc", [round(float(a), 3) for a in acc], flush=True)
     net.close()
 
 
@@ -145,6 +146,8 @@ def main():
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"fullmesh_rank_sum": False})                         # edge-list gather
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"transport": "nvls", "fullmesh_rank_sum": False})    # per-slot multimem
     check("fedavg", {}, n + 1, {"type": "fully", "num_nodes": n + 1}, b200={"transport": "nvls"})                        # uneven slots per rank
+    check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"fullmesh_two_shot": True})                          # fused reduce-scatter + all-gather
+    check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"transport": "nvls", "fullmesh_two_shot": True})     # … through the switch
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"fullmesh_two_shot": False})                         # one-shot rank sums (p2p)
     check("fedavg", {}, n, {"type": "fully", "num_nodes": n}, b200={"transport": "nvls", "fullmesh_two_shot": False})    # one-shot, multimem
     check("balance", {"gamma": 0.6, "alpha": 0.5}, n, kreg)
