@@ -375,7 +375,6 @@ class B200Network:
                 torch.mm(torch.ones(64, 64, device=self.device), torch.ones(64, 64, device=self.device))
         torch.cuda.synchronize(self.device)
         self.eval_stats = torch.zeros(max(self.V, 1), _STAT_COLS, device=self.device)
-        self.metrics_host = torch.zeros(self.placement.slots_per_rank * self.world, _STAT_COLS).pin_memory()
         self.lam_t = torch.zeros((), device=self.device)
         self.round_idx = 0
         self.epoch = 0

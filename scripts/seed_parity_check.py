@@ -1,3 +1,7 @@
+"""Round-by-round accuracy of the simulation backend vs the B200 engine in seed-parity mode (autograd path, eager, fused tape).
+
+    python scripts/seed_parity_check.py [ALGO] [JSON params]      e.g.  krum '{"num_compromised": 1}'
+"""
 import sys; import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tests'))
 import torch, json
 ALGO = sys.argv[1] if len(sys.argv) > 1 else "fedavg"
