@@ -69,3 +69,28 @@ def make_loaders(dataset_adapter, client_id: int, batch_size: int):
         return (FastTensorLoader(x, y, bs, shuffle=True, drop_last=n > bs, dataset=shard),
                 FastTensorLoader(x, y, bs, shuffle=False, dataset=shard), n)
     return DataLoader(shard, batch_size=bs, shuffle=True, drop_last=n > bs), DataLoader(shard, batch_size=bs, shuffle=False), n
+
+
+def replay_round_orders(sizes, batch_size: int, epochs: int, skip=()) -> dict:
+    """Sample orders of ONE round of local training for every client, drawn from the global torch CPU stream exactly as the simulation
+    backend's shuffling loaders draw them (clients in id order, ``skip`` = compromised clients, which do not train; per epoch one
+    int64 for the iterator's base seed, one int64 seeding a private generator, ``randperm(n)`` from it, truncated to whole batches like
+    ``drop_last``).  Used by the B200 engine's seed-parity mode; returns ``{client_id: LongTensor[epochs, nb·eb]}``."""
+    out = {}
+    for cid, n in enumerate(sizes):
+        if cid in skip:
+            continue
+        n = int(n)
+        eb = min(int(batch_size), max(2, n))
+        nb = (n // eb) if n > eb else (1 if n >= 2 else 0)
+        rows = []
+        for _ in range(epochs):
+            torch.empty((), dtype=torch.int64).random_()
+            if n == 0:
+                continue
+            g = torch.Generator()
+            g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            rows.append(torch.randperm(n, generator=g)[: nb * min(eb, n)])
+        if rows and nb > 0:
+            out[cid] = torch.stack(rows)
+    return out

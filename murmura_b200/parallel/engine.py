@@ -619,26 +619,10 @@ class B200Network:
         simulation backend's loaders draw them — nodes in id order, attackers skipped (they do not train), per epoch one int64
         for the iterator's base seed, one int64 seeding a private generator, ``randperm(n)`` from it (``data/fast_loader.py``,
         i.e. ``DataLoader(shuffle=True)``); every rank replays the whole sequence and keeps its own nodes."""
-        bs = int(self.cfg.training.batch_size)
-        by_gid = {vn.gid: vn for vn in self.nodes}
-        out: Dict[int, torch.Tensor] = {}
-        for gid in range(self.N):
-            if gid in self.compromised:
-                continue
-            n = int(self._shard_sizes[gid])
-            eb = min(bs, max(2, n))
-            nb = (n // eb) if n > eb else (1 if n >= 2 else 0)
-            rows = []
-            for _ in range(epochs):
-                torch.empty((), dtype=torch.int64).random_()
-                if n == 0:
-                    continue
-                g = torch.Generator()
-                g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
-                rows.append(torch.randperm(n, generator=g)[: nb * min(eb, n)])
-            if gid in by_gid and rows and nb > 0:
-                out[gid] = torch.stack(rows)
-        return out
+        from murmura_b200.data.fast_loader import replay_round_orders
+        mine = {vn.gid for vn in self.nodes}
+        orders = replay_round_orders(self._shard_sizes, int(self.cfg.training.batch_size), epochs, skip=self.compromised)
+        return {gid: o for gid, o in orders.items() if gid in mine}
 
     def _local_training(self, epochs: int, lr: float) -> None:
         from murmura_b200.models.mlp import EvidentialLoss
@@ -1108,26 +1092,15 @@ class B200Network:
     _NETS_BUILT = 0                                     # construction order is identical on every rank: names the host barriers
 
     def _host_barrier(self) -> None:
-        """CPU-only rendezvous through the process group's key-value store (no GPU work, no NCCL kernel).
-
-        Why: a spin-wait kernel on GPU A (``wait_epoch``, or any NCCL kernel) keeps A busy until GPU B publishes — and while A is
-        busy, a ``cudaMalloc`` on B can block, because with peer mappings enabled a new allocation has to be mapped on the peers too.
-        If B still has to allocate before its publish is enqueued (first rounds: workspaces, CUDA-graph capture), B waits for A and A
-        waits for B until the flag timeout fires and B's nodes are dropped for the round.  During the warm-up rounds every rank
-        therefore enqueues its publish FIRST, meets the others here on the host, and only then launches the wait: whatever a peer
-        still allocates afterwards, the flag this GPU spins on is already on its way."""
-        import time
+        """CPU-only rendezvous between publish and the flag wait during warm-up rounds (``parallel/hostsync.py`` explains why)."""
         from torch.distributed import distributed_c10d as c10d
+        from murmura_b200.parallel.hostsync import store_barrier
         try:
             store = c10d._get_default_store()
         except Exception:  # noqa: BLE001 - no store (single process): nothing to do
             return
         self._hb_count = getattr(self, "_hb_count", 0) + 1
-        key = f"murmura_b200/hb/{self._net_id}/{self._hb_count}"
-        store.add(key, 1)
-        deadline = time.time() + max(1.0, self.opt.flag_timeout_ms / 1000.0)
-        while int(store.add(key, 0)) < self.world and time.time() < deadline:
-            time.sleep(0.0002)
+        store_barrier(store, f"murmura_b200/hb/{self._net_id}/{self._hb_count}", self.world, max(1.0, self.opt.flag_timeout_ms / 1000.0))
 
     def _freeze_liveness(self) -> None:
         """One wait on the epoch flags decides which peers arrived; every later kernel of the round consumes that mask."""

@@ -315,3 +315,74 @@ def test_fast_tensor_loader_is_bit_identical_to_dataloader(n, bs, shuffle, drop_
             assert torch.equal(xa, xb_) and torch.equal(ya, yb_) and ya.dtype == yb_.dtype
     torch.manual_seed(9); first_ref = next(iter(ref)); torch.manual_seed(9); first_fast = next(iter(fast))       # UBAR's next(iter(loader))
     assert torch.equal(first_ref[0], first_fast[0])
+
+
+def test_replay_round_orders_matches_the_simulation_loaders_rng_consumption():
+    """Seed-parity mode of the B200 engine: ``replay_round_orders`` must draw from the global torch stream exactly like iterating
+    the simulation backend's shuffling loaders node by node (reference ``murmura/core/network.py:80-92`` + ``DataLoader(shuffle=True)``),
+    including drop_last truncation, skipped (compromised) clients and two local epochs — and leave the stream in the same state."""
+    import torch
+    from murmura_b200.data.fast_loader import FastTensorLoader, replay_round_orders
+    sizes, bs, epochs, skip = [70, 33, 5, 64, 1, 200], 32, 2, {3}
+    shards = [(torch.arange(n, dtype=torch.float32).view(n, 1), torch.arange(n)) for n in sizes]
+    torch.manual_seed(1234)
+    want = {}
+    for cid, (x, y) in enumerate(shards):
+        if cid in skip:
+            continue
+        n = len(x)
+        eb = min(bs, max(2, n))
+        loader = FastTensorLoader(x, y, eb, shuffle=True, drop_last=n > eb)
+        rows = []
+        for _ in range(epochs):
+            got = [yb for xb, yb in loader if xb.size(0) >= 2]
+            if got:
+                rows.append(torch.cat(got))
+        if rows:
+            want[cid] = torch.stack(rows)
+    tail_want = torch.rand(3)
+    torch.manual_seed(1234)
+    got = replay_round_orders(sizes, bs, epochs, skip=skip)
+    tail_got = torch.rand(3)
+    assert set(got) == set(want) == {0, 1, 2, 5}
+    for cid in want:
+        assert torch.equal(got[cid], want[cid]), cid
+    assert torch.equal(tail_got, tail_want)
+
+
+def _store_barrier_worker(rank, world, port, delays, out):
+    import time
+    import torch.distributed as dist
+    from datetime import timedelta
+    from murmura_b200.parallel.hostsync import store_barrier
+    store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0), timeout=timedelta(seconds=30))
+    time.sleep(delays[rank])
+    t0 = time.time()
+    ok = store_barrier(store, "hb/1/1", world, timeout_s=20.0)
+    out.put((rank, ok, time.time() - t0))
+    if rank == 1:                                                   # second barrier: rank 0 never arrives → timeout path
+        out.put((rank, store_barrier(store, "hb/1/2", world, timeout_s=0.3), -1.0))
+    store_barrier(store, "hb/1/done", world, timeout_s=20.0)        # keep the master alive until everybody is done
+
+
+def test_store_barrier_rendezvous_and_timeout():
+    """Host-side rendezvous used between publish and the flag wait (parallel/hostsync.py): nobody passes before the slowest rank
+    arrived, a missing rank times out instead of hanging."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    delays = [0.0, 0.0, 0.8]
+    procs = [ctx.Process(target=_store_barrier_worker, args=(r, 3, port, delays, out)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    got = [out.get(timeout=5) for _ in range(4)]
+    first = {r: (ok, dt) for r, ok, dt in got if dt >= 0}
+    assert all(ok for ok, _ in first.values()) and len(first) == 3
+    assert first[0][1] >= 0.6 and first[1][1] >= 0.6 and first[2][1] < 0.5        # the early ranks waited for the late one
+    assert [ok for r, ok, dt in got if dt < 0] == [False]
