@@ -264,7 +264,7 @@ def run_ours(args):
     torch.cuda.synchronize(device); _barrier()
     wall = _max_over_ranks(time.perf_counter() - t0, device)
     h2d = _max_over_ranks(float(net.h2d_bytes_per_round), device)
-    d2h = float(net.metrics_host.numel() * 4)
+    d2h = float(net.d2h_bytes_per_round)
     net.close()
 
     if rank == 0:

@@ -1654,6 +1654,11 @@ class B200Network:
         self._join()
         return None if enqueue_only else self._collect_metrics()
 
+    @property
+    def d2h_bytes_per_round(self) -> int:
+        """Bytes of the metric table an evaluated round copies to the host (pinned ring slot + the timed-out mask)."""
+        return int(self.placement.slots_per_rank * self.world * _STAT_COLS * 4 + 4)
+
     # ---- metrics ring (SURVEY C3): evaluated rounds leave their [N, 8] table in a pinned host ring; the host reads it LATER ----
     _RING = 64
 

@@ -386,3 +386,22 @@ def test_store_barrier_rendezvous_and_timeout():
     assert all(ok for ok, _ in first.values()) and len(first) == 3
     assert first[0][1] >= 0.6 and first[1][1] >= 0.6 and first[2][1] < 0.5        # the early ranks waited for the late one
     assert [ok for r, ok, dt in got if dt < 0] == [False]
+
+
+def test_bench_only_uses_engine_attributes_that_exist():
+    """bench.py runs on the GPU box only; guard its use of the engine's surface on the CPU (a renamed / removed attribute would
+    otherwise surface at round end)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bench = open(os.path.join(root, "bench.py")).read()
+    engine = open(os.path.join(root, "murmura_b200", "parallel", "engine.py")).read()
+    arena = open(os.path.join(root, "murmura_b200", "parallel", "arena.py")).read()
+    used = set(re.findall(r"\bnet\.([A-Za-z_]\w*)", bench))
+    assert {"train", "close", "timers", "history", "d2h_bytes_per_round", "h2d_bytes_per_round"} <= used
+    for name in used:
+        assert re.search(rf"def {name}\b|self\.{name}\b\s*[:=]|self\.{name}\b", engine), name
+    for sub in re.findall(r"\bnet\.layout\.([A-Za-z_]\w*)", bench):
+        assert re.search(rf"\b{sub}\b", arena), sub
+    for sub in re.findall(r"\bnet\.opt\.([A-Za-z_]\w*)", bench):
+        assert re.search(rf"^\s+{sub}\s*:", open(os.path.join(root, "murmura_b200", "config", "schema.py")).read(), re.M), sub
