@@ -290,3 +290,99 @@ def emulate(plan: Dict, X: np.ndarray, Y: np.ndarray, row: np.ndarray, R: Option
             row[w_off + np.arange(N) * wrow + tap * Cw + cc] += D[lt * C + cc].astype(row.dtype)
     if plan.get("ones_row") and plan.get("bias_off", -1) >= 0:
         row[plan["bias_off"] + np.arange(N)] += (alpha * dY.sum(axis=0)).astype(row.dtype)
+
+
+# =====================================================================================================================
+# NumPy emulator of the TMA-fed kernel's GEOMETRY (conv_tma.cu): tiles of whole images / row strips, one tensor-map box per tap and
+# k-block (out-of-bounds elements read as zero, ``elementStrides`` = conv stride), parity classes of strided dgrads, pixel-block
+# reductions of wgrad, and the epilogue's tile-row → output-pixel map.  No swizzle / descriptors (shape independent, GPU-tested).
+# =====================================================================================================================
+def _box(T: np.ndarray, start: Sequence[int], box: Sequence[int], es: Sequence[int]) -> np.ndarray:
+    """``cp.async.bulk.tensor`` tile mode on an N-d array given slowest-dim-first (NumPy order); ``start`` / ``box`` / ``es`` are
+    innermost-first like the tensor map.  box[i] is the bounding box in tensor elements, es[i] the traversal stride; elements
+    outside the tensor read as zero.  Returns the box slowest-dim-first with ceil(box / es) entries per dim."""
+    nd = T.ndim
+    out_shape = [-(-int(box[i]) // int(es[i])) for i in range(nd)][::-1]
+    out = np.zeros(out_shape, dtype=np.float64)
+    idx = [int(start[i]) + np.arange(out_shape[nd - 1 - i]) * int(es[i]) for i in range(nd)]       # innermost-first coordinates
+    ok = [(ix >= 0) & (ix < T.shape[nd - 1 - i]) for i, ix in enumerate(idx)]
+    sel = np.ix_(*[np.where(ok[i], idx[i], 0) for i in range(nd - 1, -1, -1)])
+    vals = T[sel]
+    mask = np.ones(out_shape, dtype=bool)
+    for axis, i in enumerate(range(nd - 1, -1, -1)):                # axis 0 = slowest dim = innermost-first index nd-1
+        shape = [1] * nd
+        shape[axis] = out_shape[axis]
+        mask = mask & ok[i].reshape(shape)
+    out[...] = np.where(mask, vals, 0.0)
+    return out
+
+
+def emulate_tma(mode: int, g: ConvGeom, tp: Dict, X: np.ndarray, Yb: np.ndarray, W: np.ndarray, bn: Optional[int] = None) -> np.ndarray:
+    """One group through the TMA geometry ``tp = tma_plan(mode, g, …)``.
+
+    F: ``X`` [B, IH, IW, Cin_pad] activations, ``W`` [Cout, KH·KW·Cin] → returns Y [B, OH, OW, Cout_pad].
+    D: ``X`` = dY [B, OH, OW, Cout_pad], ``W`` as above → returns dX [B, IH, IW, Cin_pad].
+    W: ``X`` activations, ``Yb`` = dY [B, OH, OW, Cout_pad] → returns dW [Cout, KH·KW·Cin] (without the bias row)."""
+    BNt = bn or _bn_tile(g.Cout if mode != MODE_D else g.Cin)
+    s = g.stride
+    if mode in (MODE_F, MODE_D):
+        (_, _, _, boxA, esA, _), (_, _, _, boxB, _, _) = tp["maps"]
+        C = g.Cin_pad if mode == MODE_F else g.Cout_pad
+        N = g.Cout if mode == MODE_F else g.Cin
+        OP = np.zeros((g.B, tp["OPH"], tp["OPW"], g.Cout_pad if mode == MODE_F else g.Cin_pad), dtype=np.float64)
+        written = np.zeros((g.B, tp["OPH"], tp["OPW"]), dtype=np.int32)
+        W3 = W.reshape(g.Cout, g.KH * g.KW, g.Cin)
+        for cls in tp["classes"]:
+            for mt in range(tp["mtiles"]):
+                if tp["tpi"] == 1:
+                    b0, y0 = mt * tp["Bt"], 0
+                else:
+                    b0, y0 = divmod(mt, tp["tpi"]); y0 *= tp["TH"]
+                for n0 in range(0, N, BNt):
+                    acc = np.zeros((tp["RT"], BNt), dtype=np.float64)
+                    for lt, tap in enumerate(cls["taps"]):
+                        for c0 in range(0, C, 32):
+                            xs, ys = cls["dx"][lt], y0 * tp["ystep"] + cls["dy"][lt]
+                            A = _box(X, [c0, xs, ys, b0], boxA[:4], esA[:4]).reshape(-1, 32)[: tp["RT"]]       # rows = (image, y, x)
+                            if mode == MODE_F:          # box {32, BN, 1} over {wrow, Cout, S}: B[n][c] = W[n0+n][tap·Cin + c0 + c]
+                                Wm = W.reshape(g.Cout, g.wrow)
+                                Bt_ = _box(Wm, [tap * g.Cin + c0, n0], [32, BNt], [1, 1])                       # [BN, 32]
+                            else:                       # boxes {32 cin, 1 tap, 32 cout} over {Cin, T, Cout, S}: B[n][c] = W[c0+c][tap][n0+n]
+                                Bt_ = np.zeros((BNt, 32))
+                                for a in range(BNt // 32):
+                                    blk = _box(W3, [n0 + 32 * a, tap, c0], [32, 1, 32], [1, 1, 1])               # [cout 32, 1, cin 32]
+                                    Bt_[32 * a: 32 * a + 32] = blk[:, 0, :].T
+                            acc += A @ Bt_.T
+                    hw = tp["RH"] * tp["RW"]
+                    for r in range(tp["RT"]):
+                        bi, rem = divmod(r, hw)
+                        y, x = y0 + rem // tp["RW"], rem % tp["RW"]
+                        b = b0 + bi
+                        if y < tp["RH"] and b < g.B:
+                            oy, ox = y * tp["osc"] + cls["py"], x * tp["osc"] + cls["px"]
+                            ncol = min(BNt, N - n0)
+                            OP[b, oy, ox, n0: n0 + ncol] += acc[r, :ncol]
+                            if n0 == 0:
+                                written[b, oy, ox] += 1
+        expect = 1 if mode == MODE_F or not tp.get("partial") else None
+        if expect is not None:
+            assert (written == 1).all(), "every output pixel is produced by exactly one tile row"
+        else:
+            assert (written <= 1).all()              # parity classes without taps leave their pixels to the zero fill
+        return OP
+    # ---- W ----
+    (_, _, _, boxA, esA, _), (_, _, _, boxB, esB, _) = tp["maps"]
+    taps = g.live_taps()
+    dW = np.zeros((g.Cout, g.KH * g.KW, g.Cin), dtype=np.float64)
+    for kb in range(tp["kb_total"]):
+        if tp["bpi"] == 1:
+            pb0, py0 = kb * tp["bb"], 0
+        else:
+            pb0, py0 = divmod(kb, tp["bpi"]); py0 *= tp["bh"]
+        dy_blk = _box(Yb, [0, 0, py0, pb0], [g.Cout_pad, boxB[1], boxB[2], boxB[3]], [1, 1, 1, 1]).reshape(-1, g.Cout_pad)[: tp["PK"]]
+        for tap in taps:
+            kh, kw = divmod(tap, g.KW)
+            xw = _box(X, [0, kw - g.pad, py0 * s + kh - g.pad, pb0], [g.Cin_pad, boxA[1], boxA[2], boxA[3]], [1, esA[1], esA[2], 1])
+            xw = xw.reshape(-1, g.Cin_pad)[: tp["PK"]]
+            dW[:, tap, :] += (dy_blk[:, : g.Cout].T @ xw[:, : g.Cin])
+    return dW.reshape(g.Cout, g.wrow)

@@ -126,3 +126,69 @@ def test_split_k_choice():
     assert cp.choose_splitk(ctas=8, kb_total=72) == 18
     assert cp.choose_splitk(ctas=256, kb_total=18) == 1
     assert cp.choose_splitk(ctas=8, kb_total=4) == 1
+
+
+# ---- geometry of the TMA-fed kernel (conv_tma.cu): tiles, tensor-map boxes, parity classes, pixel blocks ------------------------
+def _tma_case(B, H, W, Cin, Cout, k, s, p):
+    g = cp.ConvGeom(B=B, IH=H, IW=W, Cin=Cin, Cout=Cout, KH=k, KW=k, stride=s, pad=p)
+    torch.manual_seed(B * 131 + H * 17 + Cin + Cout + k + s)
+    x = torch.randn(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, stride=s, padding=p)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    Xn = x.detach().permute(0, 2, 3, 1).numpy()
+    Wn = w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).numpy()
+    dYn = gy.permute(0, 2, 3, 1).numpy()
+    refs = {cp.MODE_F: y.detach().permute(0, 2, 3, 1).numpy(), cp.MODE_D: x.grad.permute(0, 2, 3, 1).numpy(),
+            cp.MODE_W: w.grad.permute(0, 2, 3, 1).reshape(Cout, -1).numpy()}
+    ran = []
+    for mode in (cp.MODE_F, cp.MODE_D, cp.MODE_W):
+        tp = cp.tma_plan(mode, g, 1 << 20, 1)
+        if tp is None:
+            continue
+        out = cp.emulate_tma(mode, g, tp, dYn if mode == cp.MODE_D else Xn, dYn if mode == cp.MODE_W else None, Wn)
+        ref = refs[mode]
+        np.testing.assert_allclose(out[..., : ref.shape[-1]], ref, rtol=1e-9, atol=1e-9)
+        ran.append(mode)
+    return ran
+
+
+TMA_CASES = [
+    (2, 8, 8, 32, 64, 3, 1, 1),        # ResNet layer1-style: one image = 64 rows, two images per tile
+    (3, 4, 4, 64, 32, 3, 2, 1),        # stride 2: dgrad as four parity classes
+    (4, 1, 1, 64, 32, 3, 1, 1),        # 3×3 on a 1×1 map (centre tap only)
+    (2, 2, 2, 32, 32, 3, 2, 1),        # 2×2 → 1×1
+    (2, 16, 16, 32, 64, 3, 1, 1),      # 256 pixels per image: strips of 8 rows
+    (3, 8, 8, 32, 64, 1, 2, 0),        # 1×1 stride-2 downsample: a single parity class has taps
+    (5, 1, 1, 96, 40, 1, 1, 0),        # linear layer, Cout not a multiple of 32 (dgrad falls back to the gather kernel)
+    (2, 14, 14, 32, 64, 5, 1, 2),      # LEAF conv2: 5×5, 196 pixels per image (strips of 9 rows, the last one partial)
+    (130, 2, 2, 32, 32, 3, 1, 1),      # more images than one tile holds, partial last tile
+    (2, 16, 16, 64, 128, 3, 2, 1),     # stride-2 with strips, BN = 128
+]
+
+
+@pytest.mark.parametrize("case", TMA_CASES)
+def test_tma_geometry_matches_conv2d_and_autograd(case):
+    ran = _tma_case(*case)
+    assert cp.MODE_F in ran and cp.MODE_W in ran
+    if case[4] % 32 == 0:
+        assert cp.MODE_D in ran
+
+
+def test_tma_geometry_random_shapes():
+    """Property test over random layer geometries: whenever the planner accepts a layer for the TMA kernels, its tiles / boxes /
+    classes reproduce conv2d and its gradients exactly (fp64)."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(B=st.integers(1, 5), H=st.integers(1, 12), W=st.integers(1, 12), cin=st.sampled_from([32, 64]), cout=st.sampled_from([32, 64, 96]),
+           k=st.sampled_from([1, 3, 5]), s=st.sampled_from([1, 2]), same=st.booleans())
+    def prop(B, H, W, cin, cout, k, s, same):
+        p = k // 2 if same else 0
+        if (H + 2 * p - k) < 0 or (W + 2 * p - k) < 0:
+            return
+        _tma_case(B, H, W, cin, cout, k, s, p)
+
+    prop()
